@@ -1,0 +1,416 @@
+// HBM-bound kernels of the sampling path: GroupNorm statistics, fused normalise/AdaGN/SiLU, FIR x2
+// resampling, row softmax, layout packing.  All activations are NHWC bf16; every thread moves 16-byte
+// vectors (8 channels) so a warp touches whole 128-byte lines along the channel axis.
+#include "evc_host.h"
+#include "evc_ptx.cuh"
+
+namespace evc {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x);
+  f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z);
+  f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm statistics: per-(sample, channel) sum and sum of squares, accumulated with atomics.
+// grid = (chunks, B), block = (nvec, rows) with nvec = C/8 channel vectors.
+// ---------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C,
+                                float* __restrict__ stats, int c_total, int c_off, int pix_per_block) {
+  extern __shared__ float sred[];  // [rows][nvec][16]
+  const int nvec = blockDim.x;
+  const int v = threadIdx.x;
+  const int r = threadIdx.y;
+  const int b = blockIdx.y;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(HW, p_begin + pix_per_block);
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  const __nv_bfloat16* xb = x + (long long)b * HW * ldx + v * 8;
+  for (int p = p_begin + r; p < p_end; p += blockDim.y) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xb + (long long)p * ldx);
+    float f[8];
+    unpack8(u, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += f[j];
+      ss[j] = fmaf(f[j], f[j], ss[j]);
+    }
+  }
+  float* mine = sred + ((size_t)r * nvec + v) * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mine[j] = s[j];
+    mine[8 + j] = ss[j];
+  }
+  __syncthreads();
+  if (r == 0) {
+    for (int rr = 1; rr < blockDim.y; ++rr) {
+      const float* o = sred + ((size_t)rr * nvec + v) * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += o[j];
+        ss[j] += o[8 + j];
+      }
+    }
+    float* dst = stats + ((long long)b * c_total + c_off + v * 8) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(dst + 2 * j, s[j]);
+      atomicAdd(dst + 2 * j + 1, ss[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Normalise + (AdaGN | affine) + SiLU over the virtual concat [x0 | x1]; writes one contiguous tensor.
+// grid = (chunks, B), block = 256.  Per-channel a[c], b[c] (y = x*a + b) are built once per block in smem.
+// ---------------------------------------------------------------------------------------------
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1,
+                                int C1, int HW, const float* __restrict__ stats0, const float* __restrict__ stats1,
+                                int groups, float eps,
+                                const float* __restrict__ ss, int adagn, int silu, __nv_bfloat16* __restrict__ y,
+                                int pix_per_block) {
+  extern __shared__ float sab[];  // a[C] | b[C]
+  const int C = C0 + C1;
+  float* sa = sab;
+  float* sb = sab + C;
+  const int b = blockIdx.y;
+  const int cpg = C / groups;
+  const float inv_n = 1.f / ((float)cpg * (float)HW);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    float s = 0.f, q = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      const int cc = g * cpg + j;
+      const float* st = (cc < C0) ? stats0 + ((long long)b * C0 + cc) * 2 : stats1 + ((long long)b * C1 + (cc - C0)) * 2;
+      s += st[0];
+      q += st[1];
+    }
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float gam = adagn ? (1.f + ss[c]) : ss[c];
+    const float bet = ss[C + c];
+    sa[c] = rstd * gam;
+    sb[c] = bet - mean * rstd * gam;
+  }
+  __syncthreads();
+  const int nvec = C / 8;
+  const int nvec0 = C0 / 8;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(HW, p_begin + pix_per_block);
+  const long long total = (long long)(p_end - p_begin) * nvec;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    const int p = p_begin + (int)(i / nvec);
+    const int v = (int)(i % nvec);
+    const long long row = (long long)b * HW + p;
+    uint4 u;
+    if (v < nvec0)
+      u = *reinterpret_cast<const uint4*>(x0 + row * C0 + v * 8);
+    else
+      u = *reinterpret_cast<const uint4*>(x1 + row * C1 + (v - nvec0) * 8);
+    float f[8];
+    unpack8(u, f);
+    const int c = v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(f[j], sa[c + j], sb[c + j]);
+      f[j] = silu ? silu_f(t) : t;
+    }
+    *reinterpret_cast<uint4*>(y + row * C + c) = pack8(f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FIR [1,3,3,1] x2 resampling, separable, zero borders (upfirdn2d modes of upsample_2d / downsample_2d).
+//   up:   out[2i]   = (x[i-1] + 3 x[i]) / 4,  out[2i+1] = (3 x[i] + x[i+1]) / 4      (per axis)
+//   down: out[i]    = (x[2i-1] + 3 x[2i] + 3 x[2i+1] + x[2i+2]) / 8                  (per axis)
+// One thread = one output pixel x 8 channels.
+// ---------------------------------------------------------------------------------------------
+__global__ void fir_up_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W,
+                              int C) {
+  const int nvec = C / 8;
+  const int OH = 2 * H, OW = 2 * W;
+  const long long total = (long long)B * OH * OW * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long t = i / nvec;
+    const int ox = (int)(t % OW);
+    t /= OW;
+    const int oy = (int)(t % OH);
+    const int b = (int)(t / OH);
+    // axis taps: even -> (i-1: 1/4, i: 3/4); odd -> (i: 3/4, i+1: 1/4)
+    const int iy = oy >> 1, ix = ox >> 1;
+    const int y2 = (oy & 1) ? iy + 1 : iy - 1;
+    const int x2 = (ox & 1) ? ix + 1 : ix - 1;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const __nv_bfloat16* xb = x + (long long)b * H * W * C + v * 8;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int yy = a ? y2 : iy;
+      const float wy = a ? 0.25f : 0.75f;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int xx = c ? x2 : ix;
+        const float w = wy * (c ? 0.25f : 0.75f);
+        if (xx < 0 || xx >= W) continue;
+        const uint4 u = *reinterpret_cast<const uint4*>(xb + ((long long)yy * W + xx) * C);
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, f[j], acc[j]);
+      }
+    }
+    *reinterpret_cast<uint4*>(y + (((long long)b * OH + oy) * OW + ox) * C + v * 8) = pack8(acc);
+  }
+}
+
+__global__ void fir_down_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
+                                int W, int C) {
+  const int nvec = C / 8;
+  const int OH = H / 2, OW = W / 2;
+  const long long total = (long long)B * OH * OW * nvec;
+  const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long t = i / nvec;
+    const int ox = (int)(t % OW);
+    t /= OW;
+    const int oy = (int)(t % OH);
+    const int b = (int)(t / OH);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const __nv_bfloat16* xb = x + (long long)b * H * W * C + v * 8;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = 2 * oy - 1 + a;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int xx = 2 * ox - 1 + c;
+        if (xx < 0 || xx >= W) continue;
+        const float w = k[a] * k[c];
+        const uint4 u = *reinterpret_cast<const uint4*>(xb + ((long long)yy * W + xx) * C);
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, f[j], acc[j]);
+      }
+    }
+    *reinterpret_cast<uint4*>(y + (((long long)b * OH + oy) * OW + ox) * C + v * 8) = pack8(acc);
+  }
+}
+
+__global__ void nearest_up2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
+                                   int W, int C) {
+  const int nvec = C / 8;
+  const int OH = 2 * H, OW = 2 * W;
+  const long long total = (long long)B * OH * OW * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long t = i / nvec;
+    const int ox = (int)(t % OW);
+    t /= OW;
+    const int oy = (int)(t % OH);
+    const int b = (int)(t / OH);
+    const uint4 u = *reinterpret_cast<const uint4*>(x + (((long long)b * H + (oy >> 1)) * W + (ox >> 1)) * C + v * 8);
+    *reinterpret_cast<uint4*>(y + (((long long)b * OH + oy) * OW + ox) * C + v * 8) = u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row softmax: one warp per row, fp32 in, bf16 out.  cols % 4 == 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void softmax_rows_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, long long rows,
+                                    int cols) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* s = S + row * cols;
+  __nv_bfloat16* p = P + row * cols;
+  float m = -INFINITY;
+  for (int c = lane * 4; c < cols; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(s + c);
+    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int c = lane * 4; c < cols; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(s + c);
+    sum += __expf(v.x - m) + __expf(v.y - m) + __expf(v.z - m) + __expf(v.w - m);
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int c = lane * 4; c < cols; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(s + c);
+    uint2 o;
+    o.x = pack_bf16x2(__expf(v.x - m) * inv, __expf(v.y - m) * inv);
+    o.y = pack_bf16x2(__expf(v.z - m) * inv, __expf(v.w - m) * inv);
+    *reinterpret_cast<uint2*>(p + c) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW fp32/fp64 -> channel slice of an NHWC bf16 buffer.  One thread per pixel; reads are coalesced per
+// channel plane, writes are one short contiguous run per pixel.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_nchw_kernel(const T* __restrict__ src, int B, int C, int HW, float scale, float shift,
+                                 __nv_bfloat16* __restrict__ dst, int Cpad, int c_off) {
+  const long long total = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const int p = (int)(i % HW);
+    const T* s = src + (long long)b * C * HW + p;
+    __nv_bfloat16* d = dst + i * Cpad + c_off;
+    for (int c = 0; c < C; ++c) d[c] = __float2bfloat16_rn(fmaf((float)s[(long long)c * HW], scale, shift));
+  }
+}
+
+__global__ void inverse_transform_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = (x[i] + 1.f) / 2.f;
+    y[i] = fminf(fmaxf(v, 0.f), 1.f);
+  }
+}
+
+}  // namespace evc
+
+using namespace evc;
+
+static inline int grid_for(long long work_items, int block) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = (long long)evc_num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, float* stats,
+                            int32_t c_total, int32_t c_off, evc_stream_t stream) {
+  if (!x || !stats || B < 1 || HW < 1 || C < 8 || (C % 8) || (ldx % 8) || (c_off % 8))
+    return evc_set_error(EVC_ERR_INVALID, "evc_gn_stats: bad arguments");
+  if (reinterpret_cast<uintptr_t>(x) & 15) return evc_set_error(EVC_ERR_INVALID, "evc_gn_stats: x not 16B aligned");
+  const int nvec = C / 8;
+  if (nvec > 1024) return evc_set_error(EVC_ERR_INVALID, "evc_gn_stats: C too large");
+  int rows = 256 / nvec;
+  if (rows < 1) rows = 1;
+  if (rows > HW) rows = HW;
+  // aim for ~4 blocks per SM overall, at least `rows` pixels per block
+  const int sms = evc_num_sms();
+  int chunks = (sms * 4 + B - 1) / B;
+  int max_chunks = (HW + rows - 1) / rows;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  const int ppb = (HW + chunks - 1) / chunks;
+  chunks = (HW + ppb - 1) / ppb;
+  dim3 block(nvec, rows), grid(chunks, B);
+  const size_t smem = (size_t)rows * nvec * 16 * sizeof(float);
+  gn_stats_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C,
+                                                               stats, c_total, c_off, ppb);
+  return evc_check_launch("gn_stats_kernel");
+}
+
+extern "C" int evc_gn_apply(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int32_t HW,
+                            const float* stats0, const float* stats1, int32_t groups, float eps, const float* ss,
+                            int32_t adagn, int32_t silu, void* y, evc_stream_t stream) {
+  if (!x0 || !stats0 || (x1 != nullptr && stats1 == nullptr) || !ss || !y || B < 1 || HW < 1 || C0 < 8 || (C0 % 8) || (C1 % 8) || (x1 == nullptr && C1 != 0) ||
+      groups < 1 || ((C0 + C1) % groups))
+    return evc_set_error(EVC_ERR_INVALID, "evc_gn_apply: bad arguments");
+  const int C = C0 + C1;
+  const int sms = evc_num_sms();
+  int chunks = (sms * 8 + B - 1) / B;
+  if (chunks > HW) chunks = HW;
+  if (chunks < 1) chunks = 1;
+  const int ppb = (HW + chunks - 1) / chunks;
+  chunks = (HW + ppb - 1) / ppb;
+  dim3 grid(chunks, B);
+  const size_t smem = (size_t)2 * C * sizeof(float);
+  if (smem > 48 * 1024) return evc_set_error(EVC_ERR_INVALID, "evc_gn_apply: C too large");
+  gn_apply_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1, HW, stats0, stats1,
+      groups, eps, ss, adagn, silu, reinterpret_cast<__nv_bfloat16*>(y), ppb);
+  return evc_check_launch("gn_apply_kernel");
+}
+
+extern "C" int evc_fir_resample(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, int32_t up,
+                                evc_stream_t stream) {
+  if (!x || !y || B < 1 || H < 1 || W < 1 || C < 8 || (C % 8) || (!up && ((H | W) & 1)))
+    return evc_set_error(EVC_ERR_INVALID, "evc_fir_resample: bad arguments");
+  const long long outpix = up ? (long long)B * 4 * H * W : (long long)B * (H / 2) * (W / 2);
+  const long long items = outpix * (C / 8);
+  const int grid = grid_for(items, 256);
+  if (up)
+    fir_up_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                          reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
+  else
+    fir_down_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                            reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
+  return evc_check_launch("fir_resample");
+}
+
+extern "C" int evc_nearest_up2(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
+                               evc_stream_t stream) {
+  if (!x || !y || B < 1 || H < 1 || W < 1 || C < 8 || (C % 8))
+    return evc_set_error(EVC_ERR_INVALID, "evc_nearest_up2: bad arguments");
+  const long long items = (long long)B * 4 * H * W * (C / 8);
+  nearest_up2_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
+  return evc_check_launch("nearest_up2_kernel");
+}
+
+extern "C" int evc_softmax_rows(const float* S, void* P, int64_t rows, int32_t cols, evc_stream_t stream) {
+  if (!S || !P || rows < 1 || cols < 4 || (cols % 4)) return evc_set_error(EVC_ERR_INVALID, "evc_softmax_rows: bad arguments");
+  const int warps = 8;
+  const long long grid = (rows + warps - 1) / warps;
+  if (grid > 0x7fffffffLL) return evc_set_error(EVC_ERR_INVALID, "evc_softmax_rows: too many rows");
+  softmax_rows_kernel<<<(unsigned)grid, warps * 32, 0, (cudaStream_t)stream>>>(S, reinterpret_cast<__nv_bfloat16*>(P),
+                                                                              rows, cols);
+  return evc_check_launch("softmax_rows_kernel");
+}
+
+extern "C" int evc_pack_nchw(const void* src, int32_t src_is_f64, int32_t B, int32_t C, int32_t HW, float scale,
+                             float shift, void* dst, int32_t Cpad, int32_t c_off, evc_stream_t stream) {
+  if (!src || !dst || B < 1 || C < 1 || HW < 1 || c_off < 0 || c_off + C > Cpad)
+    return evc_set_error(EVC_ERR_INVALID, "evc_pack_nchw: bad arguments");
+  const int grid = grid_for((long long)B * HW, 256);
+  if (src_is_f64)
+    pack_nchw_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(src), B, C, HW,
+                                                                     scale, shift, reinterpret_cast<__nv_bfloat16*>(dst),
+                                                                     Cpad, c_off);
+  else
+    pack_nchw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(src), B, C, HW, scale,
+                                                                    shift, reinterpret_cast<__nv_bfloat16*>(dst), Cpad,
+                                                                    c_off);
+  return evc_check_launch("pack_nchw_kernel");
+}
+
+extern "C" int evc_fill_zero(void* p, int64_t bytes, evc_stream_t stream) {
+  if (!p || bytes < 0) return evc_set_error(EVC_ERR_INVALID, "evc_fill_zero: bad arguments");
+  cudaError_t e = cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream);
+  if (e != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
+  return EVC_OK;
+}
+
+extern "C" int evc_inverse_transform(const float* x, float* frames, int64_t n, evc_stream_t stream) {
+  if (!x || !frames || n < 1) return evc_set_error(EVC_ERR_INVALID, "evc_inverse_transform: bad arguments");
+  inverse_transform_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, frames, n);
+  return evc_check_launch("inverse_transform_kernel");
+}

@@ -1,0 +1,455 @@
+// Implicit-GEMM convolution / batched GEMM on the sm_100a tensor cores.
+//
+// One persistent, warp-specialised kernel: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer,
+// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> global).
+//   * A operand: NHWC bf16 activations fetched by 4-D TMA boxes (64 channels x TW x TH x TB pixels = one
+//     128 x 64 K-major SWIZZLE_128B tile).  A 3x3 convolution is nine shifted boxes; TMA out-of-bounds
+//     zero fill implements the zero padding, so no im2col buffer ever exists in HBM.
+//   * B operand: packed bf16 weights (N, K_total) fetched by 3-D TMA boxes (64 x BN x 1).
+//   * accumulators: fp32 in TMEM, two stages of 256 columns so the epilogue of tile i overlaps the main
+//     loop of tile i+1.
+// Replaces cuDNN conv2d / cuBLAS einsum of the reference (models/better/layers.py:89-113, 521-544;
+// models/better/layerspp.py:239-243; models/unet.py:49-63, 114-119).
+#include "evc_host.h"
+#include "evc_ptx.cuh"
+
+namespace evc {
+
+constexpr int kMaxStages = 8;
+constexpr int kABytes = 128 * 64 * 2;  // one A stage: 128 rows x 64 bf16
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
+
+struct alignas(64) GemmParams {
+  CUtensorMap a_map[3];
+  CUtensorMap b_map;
+  int n_seg;
+  int seg_taps[3];
+  int seg_kb[3];  // 64-channel blocks per tap
+  int B, H, W;
+  int TW, TH, TB;
+  int tiles_x, tiles_y, tiles_b, tiles_n;
+  int BN, N;
+  int b_batched;
+  int num_stages;
+  int rows_valid;
+  int total_kb;
+  int out_mode;
+  long long out_ld, out_bs;
+  void* out;
+  const float* bias;
+  const __nv_bfloat16* resid;
+  long long resid_ld;
+  float alpha;
+  unsigned tx_bytes;
+};
+
+__device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int& x0, int& y0, int& b0, int& n0) {
+  int tn = tile % p.tiles_n;
+  int tm = tile / p.tiles_n;
+  int tx = tm % p.tiles_x;
+  int t2 = tm / p.tiles_x;
+  int ty = t2 % p.tiles_y;
+  int tb = t2 / p.tiles_y;
+  x0 = tx * p.TW;
+  y0 = ty * p.TH;
+  b0 = tb * p.TB;
+  n0 = tn * p.BN;
+}
+
+template <typename T>
+__device__ __forceinline__ void store_chunk(const GemmParams& p, const float (&f)[32], int ncols, int n, long long pix,
+                                            int b, long long pin) {
+  // f[0..ncols) are final values for output columns n..n+ncols of pixel row `pix` (global row index),
+  // `pin` = pixel index inside sample b.
+  if (p.out_mode == EVC_OUT_BF16_ROWS) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + n;
+    if (n + ncols <= p.N && (p.N & 7) == 0 && (p.out_ld & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        if (j < ncols) {
+          uint4 u;
+          u.x = pack_bf16x2(f[j + 0], f[j + 1]);
+          u.y = pack_bf16x2(f[j + 2], f[j + 3]);
+          u.z = pack_bf16x2(f[j + 4], f[j + 5]);
+          u.w = pack_bf16x2(f[j + 6], f[j + 7]);
+          *reinterpret_cast<uint4*>(o + j) = u;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols && n + j < p.N) o[j] = __float2bfloat16_rn(f[j]);
+    }
+  } else if (p.out_mode == EVC_OUT_F32_ROWS) {
+    float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + n;
+    if (n + ncols <= p.N && (p.N & 3) == 0 && (p.out_ld & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (j < ncols) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols && n + j < p.N) o[j] = f[j];
+    }
+  } else if (p.out_mode == EVC_OUT_BF16_T) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)b * p.out_bs + pin;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols && n + j < p.N) o[(long long)(n + j) * p.out_ld] = __float2bfloat16_rn(f[j]);
+  } else {
+    float* o = reinterpret_cast<float*>(p.out) + (long long)b * p.out_bs + pin;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols && n + j < p.N) o[(long long)(n + j) * p.out_ld] = f[j];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t bar_base = base + p.num_stages * stage_bytes;
+  // barrier slots (8 B each): full[8] | empty[8] | tmem_full[2] | tmem_empty[2] | tmem base slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.n_seg; ++s) tma_prefetch_desc(&p.a_map[s]);
+    tma_prefetch_desc(&p.b_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int x0, y0, b0, n0;
+      decode_tile(p, tile, x0, y0, b0, n0);
+      const int zb = p.b_batched ? b0 : 0;
+      int kcol = 0;
+      for (int s = 0; s < p.n_seg; ++s) {
+        const int taps = p.seg_taps[s];
+        for (int t = 0; t < taps; ++t) {
+          const int dy = (taps == 9) ? (t / 3 - 1) : 0;
+          const int dx = (taps == 9) ? (t % 3 - 1) : 0;
+          for (int c = 0; c < p.seg_kb[s]; ++c) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), p.tx_bytes);
+            const uint32_t sa = base + stage * stage_bytes;
+            tma_load_4d(&p.a_map[s], sa, full_bar(stage), c * 64, x0 + dx, y0 + dy, b0);
+            tma_load_3d(&p.b_map, sa + kABytes, full_bar(stage), kcol, n0, zb);
+            kcol += 64;
+            if (++stage == p.num_stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.BN));
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * kAccStride;
+      for (int kb = 0; kb < p.total_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * stage_bytes;
+        const uint64_t da = umma_desc_sw128(sa);
+        const uint64_t db = umma_desc_sw128(sa + kABytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+          umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (kb == p.total_kb - 1) umma_commit(tfull_bar(acc));
+        if (++stage == p.num_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int dx = row % p.TW;
+    const int dy = (row / p.TW) % p.TH;
+    const int db = row / (p.TW * p.TH);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      int x0, y0, b0, n0;
+      decode_tile(p, tile, x0, y0, b0, n0);
+      const int b = b0 + db;
+      const bool valid = (row < p.rows_valid) && (b < p.B);
+      const long long pin = (long long)(y0 + dy) * p.W + (x0 + dx);
+      const long long pix = (long long)b * p.H * p.W + pin;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        const int ncols = min(32, p.BN - c0);
+        uint32_t v[32];
+        if (ncols == 32)
+          tmem_ld_32x32(taddr + c0, v);
+        else
+          tmem_ld_32x16(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int n = n0 + c0;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = (j < ncols) ? __uint_as_float(v[j]) : 0.f;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols && n + j < p.N) f[j] += __ldg(p.bias + n + j);
+          }
+          if (p.resid != nullptr) {
+            const __nv_bfloat16* r = p.resid + pix * p.resid_ld + n;
+            if (n + ncols <= p.N && (p.resid_ld & 7) == 0 && (p.N & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (j < ncols) {
+                  const uint4 u = *reinterpret_cast<const uint4*>(r + j);
+                  f[j + 0] += bf16_lo(u.x);
+                  f[j + 1] += bf16_hi(u.x);
+                  f[j + 2] += bf16_lo(u.y);
+                  f[j + 3] += bf16_hi(u.y);
+                  f[j + 4] += bf16_lo(u.z);
+                  f[j + 5] += bf16_hi(u.z);
+                  f[j + 6] += bf16_lo(u.w);
+                  f[j + 7] += bf16_hi(u.w);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols && n + j < p.N) f[j] += __bfloat162float(r[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
+          store_chunk<float>(p, f, ncols, n, pix, b, pin);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace evc
+
+// ===================================================================================== host side
+using namespace evc;
+
+struct evc_gemm_plan {
+  GemmParams p;
+  int grid;
+  int smem_bytes;
+  double flops;
+};
+
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  PFN_encodeTiled enc = evc_get_encode_tiled();
+  if (enc == nullptr) return evc_set_error(EVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  uint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf),
+             "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] ptr %p", (int)r,
+             rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+             (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0,
+             ptr);
+    return evc_set_error(EVC_ERR_CUDA, buf);
+  }
+  return EVC_OK;
+}
+
+extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_plan) {
+  if (d == nullptr || out_plan == nullptr) return evc_set_error(EVC_ERR_INVALID, "null argument");
+  *out_plan = nullptr;
+  if (d->n_seg < 1 || d->n_seg > 3) return evc_set_error(EVC_ERR_INVALID, "n_seg must be 1..3");
+  if (d->bn < 16 || d->bn > 256 || (d->bn % 16) != 0) return evc_set_error(EVC_ERR_INVALID, "bn must be 16..256, %16");
+  if (d->B < 1 || d->H < 1 || d->W < 1) return evc_set_error(EVC_ERR_INVALID, "bad output extent");
+  if (d->out == nullptr || d->w == nullptr) return evc_set_error(EVC_ERR_INVALID, "null out / w");
+  if (d->out_mode < 0 || d->out_mode > 3) return evc_set_error(EVC_ERR_INVALID, "bad out_mode");
+  if (d->w_batches != 1 && d->w_batches != d->B) return evc_set_error(EVC_ERR_INVALID, "w_batches must be 1 or B");
+
+  evc_gemm_plan* pl = new evc_gemm_plan();
+  GemmParams& p = pl->p;
+  memset(&p, 0, sizeof(p));
+  p.n_seg = d->n_seg;
+  p.B = d->B;
+  p.H = d->H;
+  p.W = d->W;
+  p.b_batched = (d->w_batches > 1) ? 1 : 0;
+  // M tile = TW x TH x TB pixels (<= 128)
+  int TW = d->W < 128 ? d->W : 128;
+  int TH = d->H < (128 / TW) ? d->H : (128 / TW);
+  if (TH < 1) TH = 1;
+  int TB = p.b_batched ? 1 : 128 / (TW * TH);
+  if (TB < 1) TB = 1;
+  if ((d->W % TW) != 0 || (d->H % TH) != 0 || (128 % TW) != 0 || TW * TH * TB > 128) {
+    delete pl;
+    return evc_set_error(EVC_ERR_INVALID, "W/H must tile into 128-pixel boxes (powers of two)");
+  }
+  p.TW = TW;
+  p.TH = TH;
+  p.TB = TB;
+  p.rows_valid = TW * TH * TB;
+  p.tiles_x = d->W / TW;
+  p.tiles_y = d->H / TH;
+  p.tiles_b = (d->B + TB - 1) / TB;
+  p.BN = d->bn;
+  p.N = d->w_rows;
+  p.tiles_n = (d->w_rows + d->bn - 1) / d->bn;
+
+  int total_kb = 0;
+  long long ktot = 0;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const evc_tensor4& a = d->a[s];
+    if (d->taps[s] != 1 && d->taps[s] != 9) {
+      delete pl;
+      return evc_set_error(EVC_ERR_INVALID, "taps must be 1 or 9");
+    }
+    if (a.ptr == nullptr || (a.C % 64) != 0 || a.W != d->W || a.H != d->H || a.B != d->B) {
+      delete pl;
+      return evc_set_error(EVC_ERR_INVALID, "A segment: C %% 64 != 0 or extent mismatch");
+    }
+    if ((reinterpret_cast<uintptr_t>(a.ptr) & 15) || (a.stride_w % 8) || (a.stride_h % 8) || (a.stride_b % 8)) {
+      delete pl;
+      return evc_set_error(EVC_ERR_INVALID, "A segment: pointer/strides must be 16-byte aligned");
+    }
+    uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+    uint64_t strides[3] = {(uint64_t)a.stride_w * 2, (uint64_t)a.stride_h * 2, (uint64_t)a.stride_b * 2};
+    uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
+    int rc = encode_map(&p.a_map[s], a.ptr, 4, dims, strides, box);
+    if (rc != EVC_OK) {
+      delete pl;
+      return rc;
+    }
+    p.seg_taps[s] = d->taps[s];
+    p.seg_kb[s] = a.C / 64;
+    total_kb += d->taps[s] * (a.C / 64);
+    ktot += (long long)d->taps[s] * a.C;
+  }
+  if (ktot != d->w_k) {
+    delete pl;
+    return evc_set_error(EVC_ERR_INVALID, "w_k does not match sum(taps*C) of the A segments");
+  }
+  p.total_kb = total_kb;
+  {
+    if ((reinterpret_cast<uintptr_t>(d->w) & 15) || (d->w_row_stride % 8) || (d->w_batches > 1 && (d->w_batch_stride % 8))) {
+      delete pl;
+      return evc_set_error(EVC_ERR_INVALID, "W: pointer/strides must be 16-byte aligned");
+    }
+    uint64_t dims[3] = {(uint64_t)d->w_k, (uint64_t)d->w_rows, (uint64_t)d->w_batches};
+    uint64_t bstride = d->w_batches > 1 ? (uint64_t)d->w_batch_stride * 2 : (uint64_t)d->w_row_stride * 2 * d->w_rows;
+    if (bstride % 16) bstride = ((bstride + 15) / 16) * 16;
+    uint64_t strides[2] = {(uint64_t)d->w_row_stride * 2, bstride};
+    uint32_t box[3] = {64, (uint32_t)d->bn, 1};
+    int rc = encode_map(&p.b_map, d->w, 3, dims, strides, box);
+    if (rc != EVC_OK) {
+      delete pl;
+      return rc;
+    }
+  }
+  p.out = d->out;
+  p.out_mode = d->out_mode;
+  p.out_ld = d->out_ld;
+  p.out_bs = d->out_bs;
+  p.bias = d->bias;
+  p.resid = reinterpret_cast<const __nv_bfloat16*>(d->resid);
+  p.resid_ld = d->resid_ld;
+  p.alpha = d->alpha;
+  const int a_box_bytes = 64 * 2 * p.rows_valid;
+  p.tx_bytes = (unsigned)(a_box_bytes + d->bn * 128);
+
+  const int stage_bytes = kABytes + d->bn * 128;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  p.num_stages = stages;
+  pl->smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+  const long long tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+  int sms = evc_num_sms();
+  int cap = d->max_ctas > 0 ? d->max_ctas : sms;
+  pl->grid = (int)(tiles < cap ? tiles : cap);
+  pl->flops = 2.0 * (double)d->B * d->H * d->W * (double)d->w_rows * (double)d->w_k;
+  *out_plan = pl;
+  return EVC_OK;
+}
+
+extern "C" int evc_gemm_plan_launch(const evc_gemm_plan* pl, const float* bias_override, evc_stream_t stream) {
+  if (pl == nullptr) return evc_set_error(EVC_ERR_INVALID, "null plan");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(evc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  if (bias_override != nullptr) {
+    GemmParams p = pl->p;
+    p.bias = bias_override;
+    evc_gemm_kernel<<<pl->grid, kThreads, pl->smem_bytes, (cudaStream_t)stream>>>(p);
+  } else {
+    evc_gemm_kernel<<<pl->grid, kThreads, pl->smem_bytes, (cudaStream_t)stream>>>(pl->p);
+  }
+  return evc_check_launch("evc_gemm_kernel");
+}
+
+extern "C" void evc_gemm_plan_destroy(evc_gemm_plan* pl) { delete pl; }
+extern "C" double evc_gemm_plan_flops(const evc_gemm_plan* pl) { return pl ? pl->flops : 0.0; }

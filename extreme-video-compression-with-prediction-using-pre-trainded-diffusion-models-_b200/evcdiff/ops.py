@@ -1,0 +1,175 @@
+"""Tensor-level wrappers over the C ABI.  torch is used for device memory and the current stream only."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (EVC_OUT_BF16_ROWS, EVC_OUT_BF16_T, EVC_OUT_F32_ROWS, EVC_OUT_F32_T, GemmDesc, PndmCoef, StepCoef,
+                   check, load, stream_ptr)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.EvcError("evcdiff kernels need CUDA tensors (no CPU fallback)")
+
+
+class GemmPlan:
+    """One implicit-GEMM launch: out = alpha * (sum_seg conv_taps(A_seg) @ W^T + bias + resid).
+
+    segs: list of (tensor viewed as (B,H,W,C) bf16 with unit channel stride, taps in {1,9})
+    w:    bf16 (N,K) shared weights or (B,N,K) per-sample operand, K contiguous
+    out:  bf16/fp32 tensor; out_mode selects row-major pixel rows or channel-major (transposed) layout
+    """
+
+    def __init__(self, segs, w, out, out_mode, out_ld, out_bs=0, bias=None, resid=None, resid_ld=0, alpha=1.0,
+                 bn=None, max_ctas=0):
+        lib = load()
+        _require_cuda(w, out, bias, resid, *[s[0] for s in segs])
+        d = GemmDesc()
+        d.n_seg = len(segs)
+        B, H, W_, _ = segs[0][0].shape
+        ktot = 0
+        for i, (a, taps) in enumerate(segs):
+            assert a.dtype == torch.bfloat16 and a.dim() == 4 and a.stride(3) == 1, "A segment must be (B,H,W,C) bf16"
+            d.a[i].ptr = a.data_ptr()
+            d.a[i].B, d.a[i].H, d.a[i].W, d.a[i].C = a.shape
+            d.a[i].stride_b, d.a[i].stride_h, d.a[i].stride_w = a.stride(0), a.stride(1), a.stride(2)
+            d.taps[i] = taps
+            ktot += taps * a.shape[3]
+        assert w.dtype == torch.bfloat16 and w.stride(-1) == 1
+        if w.dim() == 2:
+            d.w_rows, d.w_k, d.w_batches = w.shape[0], w.shape[1], 1
+            d.w_row_stride, d.w_batch_stride = w.stride(0), 0
+        else:
+            d.w_batches, d.w_rows, d.w_k = w.shape
+            d.w_batch_stride, d.w_row_stride = w.stride(0), w.stride(1)
+        assert d.w_k == ktot, f"weight K {d.w_k} != sum(taps*C) {ktot}"
+        d.w = w.data_ptr()
+        d.B, d.H, d.W = B, H, W_
+        n = d.w_rows
+        if bn is None:
+            bn = pick_bn(n)
+        d.bn = bn
+        d.out = out.data_ptr()
+        d.out_mode = out_mode
+        d.out_ld = out_ld
+        d.out_bs = out_bs
+        d.bias = bias.data_ptr() if bias is not None else None
+        if bias is not None:
+            assert bias.dtype == torch.float32 and bias.numel() >= n
+        d.resid = resid.data_ptr() if resid is not None else None
+        d.resid_ld = resid_ld
+        d.alpha = alpha
+        d.max_ctas = max_ctas
+        self._keep = (segs, w, out, bias, resid)
+        self._lib = lib
+        h = C.c_void_p()
+        check(lib.evc_gemm_plan_create(C.byref(d), C.byref(h)), "evc_gemm_plan_create")
+        self._h = h
+        self.flops = lib.evc_gemm_plan_flops(h)
+
+    def launch(self, bias_override=None):
+        check(self._lib.evc_gemm_plan_launch(self._h, _ptr(bias_override), stream_ptr()), "evc_gemm_plan_launch")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.evc_gemm_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def pick_bn(n):
+    """N tile for the 128-row UMMA: the widest of 256/192/128/64/... that divides N (else round N up to 16)."""
+    for bn in (256, 192, 128, 64, 32, 16):
+        if n % bn == 0:
+            return bn
+    return min(256, ((n + 15) // 16) * 16)
+
+
+def gn_stats(x, B, HW, C, stats, ldx=None):
+    """stats (B,C,2) fp32 += per-channel [sum, sumsq] of x (B*HW rows of C bf16)."""
+    _require_cuda(x, stats)
+    check(load().evc_gn_stats(_ptr(x), ldx or C, B, HW, C, _ptr(stats), C, 0, stream_ptr()), "evc_gn_stats")
+
+
+def gn_apply(x0, C0, x1, C1, B, HW, stats0, stats1, groups, eps, ss, adagn, silu, y):
+    _require_cuda(x0, x1, stats0, stats1, ss, y)
+    check(load().evc_gn_apply(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(stats0), _ptr(stats1), groups, eps, _ptr(ss),
+                              int(adagn), int(silu), _ptr(y), stream_ptr()), "evc_gn_apply")
+
+
+def fir_resample(x, y, B, H, W, C, up):
+    _require_cuda(x, y)
+    check(load().evc_fir_resample(_ptr(x), _ptr(y), B, H, W, C, int(up), stream_ptr()), "evc_fir_resample")
+
+
+def nearest_up2(x, y, B, H, W, C):
+    _require_cuda(x, y)
+    check(load().evc_nearest_up2(_ptr(x), _ptr(y), B, H, W, C, stream_ptr()), "evc_nearest_up2")
+
+
+def softmax_rows(S, P, rows, cols):
+    _require_cuda(S, P)
+    check(load().evc_softmax_rows(_ptr(S), _ptr(P), rows, cols, stream_ptr()), "evc_softmax_rows")
+
+
+def timestep_embedding(labels, freqs, dim, out):
+    _require_cuda(labels, freqs, out)
+    check(load().evc_timestep_embedding(_ptr(labels), _ptr(freqs), labels.numel(), dim, _ptr(out), stream_ptr()),
+          "evc_timestep_embedding")
+
+
+def linear_f32(x, W, b, y, act_in=False, act_out=False):
+    _require_cuda(x, W, b, y)
+    L, K = x.shape
+    N = W.shape[0]
+    assert W.shape[1] == K and x.is_contiguous() and W.is_contiguous() and y.is_contiguous()
+    check(load().evc_linear_f32(_ptr(x), _ptr(W), _ptr(b), _ptr(y), L, K, N, int(act_in), int(act_out), stream_ptr()),
+          "evc_linear_f32")
+
+
+def pack_nchw(src, dst, c_off=0, scale=1.0, shift=0.0):
+    """src (B,C,H,W) fp32/fp64 contiguous -> channels [c_off, c_off+C) of dst (B,H,W,Cpad) bf16."""
+    _require_cuda(src, dst)
+    assert src.is_contiguous() and dst.is_contiguous() and src.dtype in (torch.float32, torch.float64)
+    B, Cc, H, W = src.shape
+    check(load().evc_pack_nchw(_ptr(src), int(src.dtype == torch.float64), B, Cc, H * W, scale, shift, _ptr(dst),
+                               dst.shape[-1], c_off, stream_ptr()), "evc_pack_nchw")
+
+
+def fill_zero(t):
+    _require_cuda(t)
+    check(load().evc_fill_zero(_ptr(t), t.numel() * t.element_size(), stream_ptr()), "evc_fill_zero")
+
+
+def sampler_update(x, eps, noise, x_out, xin, coef: StepCoef):
+    _require_cuda(x, eps, noise, x_out, xin)
+    B, Cc, H, W = x.shape
+    cpad = xin.shape[-1] if xin is not None else Cc
+    check(load().evc_sampler_update(_ptr(x), _ptr(eps), _ptr(noise), _ptr(x_out), _ptr(xin), B, Cc, H * W, cpad,
+                                    C.byref(coef), stream_ptr()), "evc_sampler_update")
+
+
+def pndm_update(x, eps_list, x_out, et_out, xin, coef: PndmCoef):
+    _require_cuda(x, x_out, et_out, xin, *eps_list)
+    B, Cc, H, W = x.shape
+    cpad = xin.shape[-1] if xin is not None else Cc
+    arr = (C.c_void_p * 4)(*[e.data_ptr() for e in eps_list] + [None] * (4 - len(eps_list)))
+    check(load().evc_pndm_update(_ptr(x), arr, _ptr(x_out), _ptr(et_out), _ptr(xin), B, Cc, H * W, cpad,
+                                 C.byref(coef), stream_ptr()), "evc_pndm_update")
+
+
+def inverse_transform(x, frames):
+    _require_cuda(x, frames)
+    check(load().evc_inverse_transform(_ptr(x), _ptr(frames), x.numel(), stream_ptr()), "evc_inverse_transform")
+
+
+def launch_count():
+    return int(load().evc_launch_count())

@@ -1,0 +1,185 @@
+/*
+ * evcdiff.h — C ABI of libevcdiff.so, the sm_100a (B200) kernel library behind the conditional
+ * video-diffusion sampling path (models/__init__.py samplers, models/pndm.py,
+ * models/better NCSN++ UNet, models/unet.py).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - the caller owns every buffer (the library never allocates device memory);
+ *  - every entry point enqueues work on `stream` and returns without synchronising, so a whole
+ *    sampling loop can be captured in one CUDA graph;
+ *  - return value: 0 = ok, negative = evc_status (evc_last_error() gives a message);
+ *    shape / alignment violations are errors, never fallbacks.  There is no CPU path.
+ *  - activations are NHWC bf16 ("pixel rows" of C channels); sampler state x_t is NCHW fp32, the
+ *    layout the reference samplers return (models/__init__.py:339-342).
+ *
+ * The reference has no FFI on this path except one pybind op,
+ *   upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1) -> Tensor
+ *   (models/better/op/upfirdn2d.cpp:12-23), which evc_fir_resample replaces; all other entry points
+ * replace the torch ops named next to them.
+ */
+#ifndef EVCDIFF_H_
+#define EVCDIFF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* evc_stream_t; /* cudaStream_t */
+
+enum evc_status {
+  EVC_OK = 0,
+  EVC_ERR_INVALID = -1, /* bad shape / alignment / argument */
+  EVC_ERR_CUDA = -2,    /* a CUDA runtime / driver call failed */
+  EVC_ERR_UNSUPPORTED = -3
+};
+
+int evc_version(void);
+const char* evc_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t evc_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense contractions: implicit-GEMM convolution / batched GEMM on tcgen05 tensor cores.
+ * Replaces nn.Conv2d 3x3 / 1x1 (models/better/layers.py:89-113), NIN (layers.py:535-544), the
+ * attention einsums (layerspp.py:239-243) and models/unet.py Nin / einsum (unet.py:49-63,114-119).
+ *
+ *   out[b, y, x, n] = alpha * ( sum_seg sum_tap sum_c  A_seg[b, y+dy, x+dx, c] * Wt[zb, n, k(seg,tap,c)]
+ *                               + bias[n] + resid[b, y, x, n] )
+ *
+ * A segments: up to 3 bf16 tensors viewed as (B, H, W, C) with element strides; taps = 1 (1x1 / GEMM)
+ * or 9 (3x3, zero padding 1).  C must be a multiple of 64.  Several segments implement a virtual
+ * channel concat and the fused 1x1 skip branch of a residual block (extra K).
+ * Wt: bf16 (w_batches, N, K_total), K contiguous, K order = segment-major, tap-major, channel-minor.
+ * w_batches is 1 (shared weights) or B (per-sample B operand, e.g. K / V^T in attention; then the
+ * output tile never mixes samples).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct evc_tensor4 {
+  const void* ptr;    /* bf16 */
+  int32_t C, W, H, B; /* extents, channel innermost */
+  int64_t stride_w, stride_h, stride_b; /* element strides (channel stride is 1) */
+} evc_tensor4;
+
+enum evc_out_mode {
+  EVC_OUT_BF16_ROWS = 0, /* out[(b*H*W + y*W + x) * out_ld + n]            bf16 */
+  EVC_OUT_F32_ROWS = 1,  /* same addressing, fp32                              */
+  EVC_OUT_BF16_T = 2,    /* out[b*out_bs + n*out_ld + (y*W + x)]           bf16 (channel-major / transposed) */
+  EVC_OUT_F32_T = 3      /* same addressing, fp32 (NCHW result of the last conv) */
+};
+
+typedef struct evc_gemm_desc {
+  int32_t n_seg;
+  evc_tensor4 a[3];
+  int32_t taps[3];
+  const void* w;
+  int32_t w_rows;    /* N */
+  int32_t w_k;       /* K_total = sum_seg taps*C */
+  int32_t w_batches; /* 1 or B */
+  int64_t w_row_stride, w_batch_stride; /* elements */
+  int32_t B, H, W;   /* output extent (== input extent, stride 1) */
+  int32_t bn;        /* N tile: multiple of 16, 16..256 */
+  void* out;
+  int32_t out_mode;
+  int64_t out_ld, out_bs;
+  const float* bias;  /* N floats or NULL */
+  const void* resid;  /* bf16 rows [(b*H*W + y*W + x) * resid_ld + n] or NULL */
+  int64_t resid_ld;
+  float alpha;
+  int32_t max_ctas;   /* 0 = number of SMs */
+} evc_gemm_desc;
+
+typedef struct evc_gemm_plan evc_gemm_plan;
+
+/* Validates, encodes the TMA descriptors (host side, no device work) and returns a reusable plan. */
+int evc_gemm_plan_create(const evc_gemm_desc* desc, evc_gemm_plan** plan);
+/* bias_override: NULL = use desc->bias. Used for per-label bias tables (models/unet.py:87-88). */
+int evc_gemm_plan_launch(const evc_gemm_plan* plan, const float* bias_override, evc_stream_t stream);
+void evc_gemm_plan_destroy(evc_gemm_plan* plan);
+/* 2 * M * N * K of one launch (dense FLOPs, for the roofline) */
+double evc_gemm_plan_flops(const evc_gemm_plan* plan);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm statistics and the fused normalise / AdaGN / affine / SiLU pass.
+ * Replaces nn.GroupNorm + get_act_norm (layerspp.py:465-549) and Normalize+Swish (unet.py:44-46,90-95).
+ * ---------------------------------------------------------------------------------------------- */
+/* stats[(b*c_total + c_off + c)*2 + {0,1}] += {sum, sum of squares} over the HW pixels of x (bf16 rows,
+ * row stride ldx).  stats must be zeroed by the caller (evc_fill_zero). C % 8 == 0. */
+int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, float* stats, int32_t c_total,
+                 int32_t c_off, evc_stream_t stream);
+
+/* y[b, p, c] = act( (x[b,p,c] - mean_g) * rstd_g * (gamma'[c]) + beta'[c] ), group g = c / (C/groups) over the
+ * concatenation [x0 | x1] (x1 may be NULL).  mean/rstd come from the per-channel sums `stats0` (B,C0,2) and
+ * `stats1` (B,C1,2) written by evc_gn_stats (biased variance, eps); a group may straddle the concat boundary.
+ *   adagn != 0: gamma' = 1 + ss[c], beta' = ss[C + c]          (ss = Dense_0(SiLU(temb)) row, 2*C floats)
+ *   adagn == 0: gamma' = ss[c], beta' = ss[C + c]              (GroupNorm affine weight | bias)
+ * silu != 0 applies x*sigmoid(x).  Output bf16 rows with row stride C (materialises the concat). */
+int evc_gn_apply(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int32_t HW, const float* stats0,
+                 const float* stats1, int32_t groups, float eps, const float* ss, int32_t adagn, int32_t silu,
+                 void* y, evc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * FIR [1,3,3,1] x2 resampling (upfirdn2d modes used by upsample_2d / downsample_2d,
+ * up_or_down_sampling.py:196-258; kernels op/upfirdn2d_kernel.cu:107-207).  NHWC bf16 in/out.
+ * up != 0: (B,H,W,C) -> (B,2H,2W,C); else (B,H,W,C) -> (B,H/2,W/2,C).
+ * ---------------------------------------------------------------------------------------------- */
+int evc_fir_resample(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, int32_t up,
+                     evc_stream_t stream);
+
+/* nearest-neighbour x2 upsample, NHWC bf16 (models/unet.py:123-131) */
+int evc_nearest_up2(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, evc_stream_t stream);
+
+/* row softmax: P[r, :] = softmax(S[r, :]) ; S fp32 (already scaled), P bf16 (layerspp.py:241, unet.py:117) */
+int evc_softmax_rows(const float* S, void* P, int64_t rows, int32_t cols, evc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Time embedding (layers.py:504-518, ncsnpp_more.py:277-281) — evaluated once per distinct label.
+ * ---------------------------------------------------------------------------------------------- */
+/* out[l, :] = [sin(t_l * f_j) | cos(t_l * f_j)], f_j = freqs[j], j < dim/2 ; fp32 */
+int evc_timestep_embedding(const float* labels, const float* freqs, int32_t L, int32_t dim, float* out,
+                           evc_stream_t stream);
+/* y[l, n] = act_out( sum_k act_in(x[l,k]) * W[n,k] + b[n] ), fp32, act flags: 0 none, 1 SiLU */
+int evc_linear_f32(const float* x, const float* W, const float* b, float* y, int32_t L, int32_t K, int32_t N,
+                   int32_t act_in, int32_t act_out, evc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout / sampler-state kernels.
+ * ---------------------------------------------------------------------------------------------- */
+/* NCHW (fp32 or fp64) -> channels [c_off, c_off+C) of an NHWC bf16 buffer with Cpad channels.
+ * v = scale * src + shift (data_transform 2x-1 fused, function.py:62-63). */
+int evc_pack_nchw(const void* src, int32_t src_is_f64, int32_t B, int32_t C, int32_t HW, float scale, float shift,
+                  void* dst, int32_t Cpad, int32_t c_off, evc_stream_t stream);
+int evc_fill_zero(void* p, int64_t bytes, evc_stream_t stream);
+
+/* One sampler update, NCHW fp32 state (models/__init__.py:289-335 ddpm, :166-169 ddim, :196/:333-335 denoise):
+ *   mode 0:  x0 = k0*(x - k1*eps); if clip: x0 = clamp(x0,-1,1);  x' = c_x0*x0 + c_x*x + c_eps*eps + c_noise*noise
+ *   mode 1:  x' = x - k1*eps                                    (final denoise)
+ * also writes bf16(x') into channels [0,C) of the NHWC UNet input `xin` (row stride Cpad). noise may be NULL
+ * when c_noise == 0. x_out may alias x. */
+typedef struct evc_step_coef {
+  int32_t mode, clip;
+  float k0, k1, c_x0, c_x, c_eps, c_noise;
+} evc_step_coef;
+int evc_sampler_update(const float* x, const float* eps, const float* noise, float* x_out, void* xin, int32_t B,
+                       int32_t C, int32_t HW, int32_t Cpad, const evc_step_coef* coef_host, evc_stream_t stream);
+
+/* PNDM transfer with a fused linear multistep combination (models/pndm.py:19-33, :15, :47):
+ *   et = w_scale * sum_i w[i]*e[i] (n_e <= 4; evaluated left to right) ; x' = x + d*(p*x - q*et) ; clip -> clamp(x',-1,1)
+ * writes x' (fp32 NCHW) to x_out, optionally et to et_out, and bf16(x') into xin. */
+typedef struct evc_pndm_coef {
+  int32_t n_e, clip;
+  float w[4];
+  float w_scale; /* et = w_scale * sum_i w[i]*e[i] : 1/6 (Runge-Kutta), 1/24 (Adams-Bashforth), 1 (plain) */
+  float d, p, q;
+} evc_pndm_coef;
+int evc_pndm_update(const float* x, const float* const* e_host, float* x_out, float* et_out, void* xin, int32_t B,
+                    int32_t C, int32_t HW, int32_t Cpad, const evc_pndm_coef* coef_host, evc_stream_t stream);
+
+/* frames = clamp((x+1)/2, 0, 1), NCHW fp32 -> NCHW fp32 (inverse_data_transform, function.py:73-82) */
+int evc_inverse_transform(const float* x, float* frames, int64_t n, evc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVCDIFF_H_ */

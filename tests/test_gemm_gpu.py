@@ -1,0 +1,125 @@
+"""GPU parity of the tcgen05 implicit-GEMM kernel (evc_gemm_*) against plain torch fp32 on the same bf16 inputs.
+
+Tolerances: fp32 outputs rel-L2 <= 2e-5 (fp32 accumulation, different summation order);
+bf16 outputs rel-L2 <= 4e-3 (one bf16 rounding of the result, 2^-9 relative per element).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from evcdiff import ops
+    return ops
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def ref_conv(segs, w, bias, resid, alpha):
+    """segs: list of ((B,H,W,C) bf16, taps); w: (N, K) bf16 with K = seg-major, tap-major, channel-minor."""
+    out = None
+    k = 0
+    for a, taps in segs:
+        Cc = a.shape[3]
+        x = a.float().permute(0, 3, 1, 2)
+        wk = w[:, k:k + taps * Cc].float()
+        if taps == 9:
+            ww = wk.reshape(-1, 3, 3, Cc).permute(0, 3, 1, 2)
+            y = F.conv2d(x, ww, padding=1)
+        else:
+            y = F.conv2d(x, wk.reshape(-1, Cc, 1, 1))
+        out = y if out is None else out + y
+        k += taps * Cc
+    if bias is not None:
+        out = out + bias.view(1, -1, 1, 1)
+    if resid is not None:
+        out = out + resid.float().permute(0, 3, 1, 2)
+    return out * alpha  # NCHW fp32
+
+
+CASES = [
+    # name, B, H, W, [(C, taps)], N, out_mode, bias, resid, alpha
+    ("gemm_k64", 1, 1, 128, [(64, 1)], 64, 1, False, False, 1.0),
+    ("gemm_k256_n192", 2, 1, 256, [(256, 1)], 192, 1, True, False, 1.0),
+    ("conv3_w128", 1, 128, 128, [(64, 9)], 192, 0, True, False, 1.0),
+    ("conv3_w64", 2, 64, 64, [(192, 9)], 192, 0, True, True, 0.70710678),
+    ("conv3_w32_n384", 3, 32, 32, [(192, 9)], 384, 0, True, False, 1.0),
+    ("conv3_w16_n576", 3, 16, 16, [(384, 9)], 576, 0, True, False, 1.0),
+    ("conv3_w8_n768", 5, 8, 8, [(576, 9)], 768, 0, True, True, 0.70710678),
+    ("conv3_w4", 9, 4, 4, [(128, 9)], 256, 1, True, False, 1.0),
+    ("conv3_w2", 33, 2, 2, [(64, 9)], 128, 1, True, False, 1.0),
+    ("res_fused_skip", 2, 32, 32, [(384, 9), (192, 1), (192, 1)], 384, 0, True, False, 0.70710678),
+    ("conv_out15_nchw", 2, 128, 128, [(192, 9)], 15, 3, True, False, 1.0),
+    ("conv_in_pad64", 2, 128, 128, [(64, 9)], 192, 0, True, False, 1.0),
+    ("nin_T", 2, 32, 32, [(384, 1)], 384, 2, True, False, 1.0),
+    ("many_tiles", 8, 64, 64, [(192, 9)], 192, 0, True, False, 1.0),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_gemm(case):
+    ops = _setup()
+    name, B, H, W, segspec, N, out_mode, use_bias, use_resid, alpha = case
+    g = torch.Generator(device="cuda").manual_seed(hash(name) % 2**31)
+    segs = [(torch.randn(B, H, W, Cc, device="cuda", generator=g).bfloat16(), taps) for Cc, taps in segspec]
+    K = sum(Cc * taps for Cc, taps in segspec)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) if use_bias else None
+    resid = torch.randn(B, H, W, N, device="cuda", generator=g).bfloat16() if use_resid else None
+    ref = ref_conv(segs, w, bias, resid, alpha)
+    if out_mode in (0, 1):
+        out = torch.full((B, H, W, N), float("nan"), device="cuda",
+                         dtype=torch.bfloat16 if out_mode == 0 else torch.float32)
+        plan = ops.GemmPlan(segs, w, out, out_mode, out_ld=N, bias=bias, resid=resid, resid_ld=N, alpha=alpha)
+    else:
+        out = torch.full((B, N, H, W), float("nan"), device="cuda",
+                         dtype=torch.bfloat16 if out_mode == 2 else torch.float32)
+        plan = ops.GemmPlan(segs, w, out, out_mode, out_ld=H * W, out_bs=N * H * W, bias=bias, resid=resid,
+                            resid_ld=N, alpha=alpha)
+    plan.launch()
+    torch.cuda.synchronize()
+    got = out.float().permute(0, 3, 1, 2) if out_mode in (0, 1) else out.float()
+    assert torch.isfinite(got).all(), f"{name}: non-finite / unwritten outputs"
+    err = rel_l2(got, ref)
+    tol = 4e-3 if out_mode in (0, 2) else 2e-5
+    assert err < tol, f"{name}: rel-L2 {err:.3e} > {tol}"
+
+
+def test_batched_b_operand():
+    """Per-sample B operand (attention QK^T and PV shapes): out[b] = A[b] @ Wb[b]^T."""
+    ops = _setup()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for (B, M, K, N) in [(3, 1024, 192, 1024), (4, 256, 192, 256), (5, 64, 192, 64), (3, 1024, 1024, 192)]:
+        a = torch.randn(B, 1, M, K, device="cuda", generator=g).bfloat16()
+        wb = (torch.randn(B, N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+        out = torch.full((B, M, N), float("nan"), device="cuda", dtype=torch.float32)
+        plan = ops.GemmPlan([(a, 1)], wb, out, 1, out_ld=N, alpha=0.5)
+        plan.launch()
+        torch.cuda.synchronize()
+        ref = 0.5 * torch.bmm(a[:, 0].float(), wb.float().transpose(1, 2))
+        assert torch.isfinite(out).all()
+        assert rel_l2(out, ref) < 2e-5, (B, M, K, N, rel_l2(out, ref))
+
+
+def test_strided_views_and_repeat_launch():
+    """A/W given as strided views (head slices of a fused QK buffer); plan relaunch is idempotent."""
+    ops = _setup()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, Npix, Cc = 2, 256, 384
+    qk = torch.randn(B, Npix, 2 * Cc, device="cuda", generator=g).bfloat16()
+    h = 1
+    q = qk[:, :, h * 192:(h + 1) * 192].unsqueeze(1)  # (B,1,N,192) view
+    k = qk[:, :, Cc + h * 192:Cc + (h + 1) * 192]  # (B,N,192) view
+    out = torch.zeros(B, Npix, Npix, device="cuda", dtype=torch.float32)
+    plan = ops.GemmPlan([(q, 1)], k, out, 1, out_ld=Npix, alpha=192 ** -0.5)
+    for _ in range(3):
+        plan.launch()
+    torch.cuda.synchronize()
+    ref = torch.bmm(q[:, 0].float(), k.float().transpose(1, 2)) * 192 ** -0.5
+    assert rel_l2(out, ref) < 2e-5
