@@ -23,16 +23,21 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------
-// GroupNorm statistics: per-(sample, channel) sum and sum of squares, accumulated with atomics.
+// GroupNorm statistics: per-(sample, channel) sum and sum of squares.  Deterministic two-level reduction:
+// every block writes its partial sums to `partials`, takes a ticket, and the last block of a sample adds the
+// partials in a fixed order (no floating-point atomics, so graph replays are bit-identical).
 // grid = (chunks, B), block = (nvec, rows) with nvec = C/8 channel vectors.
 // ---------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C,
-                                float* __restrict__ stats, int c_total, int c_off, int pix_per_block) {
+                                float* __restrict__ stats, int c_total, int c_off, int pix_per_block,
+                                float* __restrict__ partials, unsigned* __restrict__ tickets) {
   extern __shared__ float sred[];  // [rows][nvec][16]
+  __shared__ unsigned s_last;
   const int nvec = blockDim.x;
   const int v = threadIdx.x;
   const int r = threadIdx.y;
   const int b = blockIdx.y;
+  const int chunks = gridDim.x;
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(HW, p_begin + pix_per_block);
   float s[8], ss[8];
@@ -56,6 +61,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
     mine[8 + j] = ss[j];
   }
   __syncthreads();
+  float* part = partials + ((long long)b * chunks + blockIdx.x) * (long long)C * 2;
   if (r == 0) {
     for (int rr = 1; rr < blockDim.y; ++rr) {
       const float* o = sred + ((size_t)rr * nvec + v) * 16;
@@ -65,13 +71,28 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
         ss[j] += o[8 + j];
       }
     }
-    float* dst = stats + ((long long)b * c_total + c_off + v * 8) * 2;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(dst + 2 * j, s[j]);
-      atomicAdd(dst + 2 * j + 1, ss[j]);
-    }
+    float4* dst = reinterpret_cast<float4*>(part + v * 16);
+    dst[0] = make_float4(s[0], ss[0], s[1], ss[1]);
+    dst[1] = make_float4(s[2], ss[2], s[3], ss[3]);
+    dst[2] = make_float4(s[4], ss[4], s[5], ss[5]);
+    dst[3] = make_float4(s[6], ss[6], s[7], ss[7]);
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) s_last = (atomicAdd(tickets + b, 1u) == (unsigned)(chunks - 1)) ? 1u : 0u;
+  __syncthreads();
+  if (s_last == 0u) return;
+  __threadfence();
+  // last block of sample b: fixed-order sum over the chunks, 2*C outputs spread over the whole block
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  const float* pb = partials + (long long)b * chunks * (long long)C * 2;
+  for (int i = tid; i < 2 * C; i += nthr) {
+    float acc = 0.f;
+    for (int k = 0; k < chunks; ++k) acc += __ldcg(pb + (long long)k * C * 2 + i);
+    stats[((long long)b * c_total + c_off) * 2 + i] = acc;
+  }
+  if (tid == 0) tickets[b] = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -303,11 +324,23 @@ static inline int grid_for(long long work_items, int block) {
   return (int)g;
 }
 
+extern "C" int evc_gn_stats_workspace(int32_t B, int32_t HW, int32_t C, int64_t* bytes) {
+  if (!bytes || B < 1 || HW < 1 || C < 8) return evc_set_error(EVC_ERR_INVALID, "evc_gn_stats_workspace: bad arguments");
+  // tickets (B * 4 bytes, rounded to 256) + partial sums for the largest grid evc_gn_stats can pick
+  const long long chunks = (long long)evc_num_sms() * 4 + 1;
+  const long long per = ((long long)B * 4 + 255) / 256 * 256;
+  long long c = chunks < HW ? chunks : HW;
+  *bytes = per + (long long)B * c * C * 2 * (long long)sizeof(float);
+  return EVC_OK;
+}
+
 extern "C" int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, float* stats,
-                            int32_t c_total, int32_t c_off, evc_stream_t stream) {
-  if (!x || !stats || B < 1 || HW < 1 || C < 8 || (C % 8) || (ldx % 8) || (c_off % 8))
+                            int32_t c_total, int32_t c_off, void* workspace, int64_t workspace_bytes,
+                            evc_stream_t stream) {
+  if (!x || !stats || !workspace || B < 1 || HW < 1 || C < 8 || (C % 8) || (ldx % 8) || (c_off % 8))
     return evc_set_error(EVC_ERR_INVALID, "evc_gn_stats: bad arguments");
-  if (reinterpret_cast<uintptr_t>(x) & 15) return evc_set_error(EVC_ERR_INVALID, "evc_gn_stats: x not 16B aligned");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15))
+    return evc_set_error(EVC_ERR_INVALID, "evc_gn_stats: x / workspace not 16B aligned");
   const int nvec = C / 8;
   if (nvec > 1024) return evc_set_error(EVC_ERR_INVALID, "evc_gn_stats: C too large");
   int rows = 256 / nvec;
@@ -321,10 +354,15 @@ extern "C" int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, i
   if (chunks < 1) chunks = 1;
   const int ppb = (HW + chunks - 1) / chunks;
   chunks = (HW + ppb - 1) / ppb;
+  const long long tick_bytes = ((long long)B * 4 + 255) / 256 * 256;
+  const long long need = tick_bytes + (long long)B * chunks * C * 2 * (long long)sizeof(float);
+  if (workspace_bytes < need) return evc_set_error(EVC_ERR_INVALID, "evc_gn_stats: workspace too small");
+  unsigned* tickets = reinterpret_cast<unsigned*>(workspace);
+  float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + tick_bytes);
   dim3 block(nvec, rows), grid(chunks, B);
   const size_t smem = (size_t)rows * nvec * 16 * sizeof(float);
   gn_stats_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C,
-                                                               stats, c_total, c_off, ppb);
+                                                               stats, c_total, c_off, ppb, partials, tickets);
   return evc_check_launch("gn_stats_kernel");
 }
 

@@ -26,7 +26,8 @@ struct alignas(64) GemmParams {
   CUtensorMap b_map;
   int n_seg;
   int seg_taps[3];
-  int seg_kb[3];  // 64-channel blocks per tap
+  int seg_kb[3];  // 64-channel blocks per tap (last one may be partial: TMA zero-fills the A columns)
+  int seg_c[3];   // channels per tap
   int B, H, W;
   int TW, TH, TB;
   int tiles_x, tiles_y, tiles_b, tiles_n;
@@ -154,10 +155,11 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       int x0, y0, b0, n0;
       decode_tile(p, tile, x0, y0, b0, n0);
       const int zb = p.b_batched ? b0 : 0;
-      int kcol = 0;
+      int kbase = 0;
       for (int s = 0; s < p.n_seg; ++s) {
         const int taps = p.seg_taps[s];
         for (int t = 0; t < taps; ++t) {
+          const int ktap = kbase + t * p.seg_c[s];
           const int dy = (taps == 9) ? (t / 3 - 1) : 0;
           const int dx = (taps == 9) ? (t % 3 - 1) : 0;
           for (int c = 0; c < p.seg_kb[s]; ++c) {
@@ -165,14 +167,14 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
             mbar_expect_tx(full_bar(stage), p.tx_bytes);
             const uint32_t sa = base + stage * stage_bytes;
             tma_load_4d(&p.a_map[s], sa, full_bar(stage), c * 64, x0 + dx, y0 + dy, b0);
-            tma_load_3d(&p.b_map, sa + kABytes, full_bar(stage), kcol, n0, zb);
-            kcol += 64;
+            tma_load_3d(&p.b_map, sa + kABytes, full_bar(stage), ktap + c * 64, n0, zb);
             if (++stage == p.num_stages) {
               stage = 0;
               phase ^= 1u;
             }
           }
         }
+        kbase += taps * p.seg_c[s];
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -364,9 +366,9 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
       delete pl;
       return evc_set_error(EVC_ERR_INVALID, "taps must be 1 or 9");
     }
-    if (a.ptr == nullptr || (a.C % 64) != 0 || a.W != d->W || a.H != d->H || a.B != d->B) {
+    if (a.ptr == nullptr || (a.C % 8) != 0 || a.C < 8 || a.W != d->W || a.H != d->H || a.B != d->B) {
       delete pl;
-      return evc_set_error(EVC_ERR_INVALID, "A segment: C %% 64 != 0 or extent mismatch");
+      return evc_set_error(EVC_ERR_INVALID, "A segment: C % 8 != 0 or extent mismatch");
     }
     if ((reinterpret_cast<uintptr_t>(a.ptr) & 15) || (a.stride_w % 8) || (a.stride_h % 8) || (a.stride_b % 8)) {
       delete pl;
@@ -381,8 +383,9 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
       return rc;
     }
     p.seg_taps[s] = d->taps[s];
-    p.seg_kb[s] = a.C / 64;
-    total_kb += d->taps[s] * (a.C / 64);
+    p.seg_kb[s] = (a.C + 63) / 64;
+    p.seg_c[s] = a.C;
+    total_kb += d->taps[s] * ((a.C + 63) / 64);
     ktot += (long long)d->taps[s] * a.C;
   }
   if (ktot != d->w_k) {

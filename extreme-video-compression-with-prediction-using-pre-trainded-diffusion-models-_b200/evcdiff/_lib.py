@@ -51,7 +51,8 @@ SIGNATURES = {
     "evc_gemm_plan_launch": (C.c_int, [_vp, _vp, _vp]),
     "evc_gemm_plan_destroy": (None, [_vp]),
     "evc_gemm_plan_flops": (C.c_double, [_vp]),
-    "evc_gn_stats": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp]),
+    "evc_gn_stats_workspace": (C.c_int, [_i32, _i32, _i32, C.POINTER(C.c_int64)]),
+    "evc_gn_stats": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
     "evc_gn_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _vp, _i32, _i32, _vp, _vp]),
     "evc_fir_resample": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evc_nearest_up2": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

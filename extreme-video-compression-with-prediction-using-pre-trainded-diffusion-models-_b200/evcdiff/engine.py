@@ -1,0 +1,400 @@
+"""Execution plans for one UNet evaluation on the CUDA kernels of libevcdiff.so.
+
+An engine is built once per (model, batch size): it repacks the reference-layout state dict into bf16 K-major
+GEMM operands, allocates every activation buffer (NHWC bf16) up front, encodes the TMA descriptors and records
+the launch sequence.  `forward(label_index)` then only enqueues kernels -- no allocation, no host sync -- so a
+whole sampling loop can be captured in a single CUDA graph.
+
+Layout decisions (DESIGN.md has the full table):
+  activations   (B, H, W, C) bf16, C contiguous; UNet input padded to 64 channels [x_t(15) | cond(6) | 0]
+  weights       conv3x3 (Cout,Cin,3,3) -> (Cout, 9*Cin) tap-major/channel-minor bf16; 1x1 / NIN -> (Cout, Cin)
+  residual 1x1  folded into the block's second conv as extra K segments (bias = b1 + b2)
+  GroupNorm     per-(sample, channel) [sum, sumsq] fp32, memoised per tensor (a skip tensor is reduced once)
+  AdaGN         scale/shift rows of a per-label table evaluated before the loop (labels are batch-uniform)
+"""
+import math
+
+import torch
+
+from . import ops
+from ._lib import EVC_OUT_BF16_ROWS, EVC_OUT_BF16_T, EVC_OUT_F32_ROWS, EVC_OUT_F32_T, EvcError
+
+CIN_PAD = 64
+RSQRT2 = 1.0 / math.sqrt(2.0)
+
+
+def gn_groups(ch):
+    g = min(ch // 4, 32)
+    while ch % g != 0:
+        g -= 1
+    return g
+
+
+class Act:
+    """NHWC bf16 activation with lazily computed GroupNorm statistics."""
+    __slots__ = ("t", "B", "H", "W", "C", "stats")
+
+    def __init__(self, t):
+        self.t = t
+        self.B, self.H, self.W, self.C = t.shape
+        self.stats = None
+
+
+class Pool:
+    """Static scratch reuse: buffers are handed out at plan-build time; stream order makes reuse safe."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free = {}
+        self.bytes = 0
+
+    def get(self, shape, dtype=torch.bfloat16):
+        key = (tuple(shape), dtype)
+        lst = self.free.get(key)
+        if lst:
+            return lst.pop()
+        t = torch.zeros(shape, dtype=dtype, device=self.device)
+        self.bytes += t.numel() * t.element_size()
+        return t
+
+    def put(self, t):
+        self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+
+def pack_conv3(w, cin_pad=None):
+    """(Cout, Cin, 3, 3) fp32 -> (Cout, 9*Cin') bf16, K = tap-major (ky,kx), channel-minor."""
+    co, ci, kh, kw = w.shape
+    w = w.permute(0, 2, 3, 1)  # co, ky, kx, ci
+    if cin_pad is not None and cin_pad != ci:
+        w = torch.nn.functional.pad(w, (0, cin_pad - ci))
+    return w.reshape(co, -1).to(torch.bfloat16).contiguous()
+
+
+class EngineBase:
+    def __init__(self, device, B, H):
+        if torch.device(device).type != "cuda":
+            raise EvcError("evcdiff engines run on CUDA devices only (no CPU fallback)")
+        self.device = torch.device(device)
+        self.B, self.H = B, H
+        self.pool = Pool(self.device)
+        self.ops = []  # list of callables(label_idx)
+        self.stats_slices = []  # (offset, numel) in the stats arena
+        self.stats_total = 0
+        self.flops = 0.0
+        self.n_launch = 0
+        self.taps = {}
+        self._keep = []
+        self._stat_acts = []
+        self.ws_bytes = 256
+
+    # ----------------------------------------------------------------- recording helpers
+    def _op(self, fn):
+        self.ops.append(fn)
+        self.n_launch += 1
+
+    def new_act(self, H, W, C, scratch=True):
+        t = self.pool.get((self.B, H, W, C)) if scratch else torch.zeros((self.B, H, W, C), dtype=torch.bfloat16,
+                                                                         device=self.device)
+        return Act(t)
+
+    def release(self, *acts):
+        for a in acts:
+            if a is not None:
+                self.pool.put(a.t)
+
+    def ensure_stats(self, a):
+        if a.stats is not None:
+            return
+        n = a.B * a.C * 2
+        a.stats = ("slice", self.stats_total, n)
+        self.stats_total += n
+        self._stat_acts.append(a)
+        act = a
+
+        self.ws_bytes = max(self.ws_bytes, ops.gn_stats_workspace_bytes(act.B, act.H * act.W, act.C))
+
+        def run(_):
+            ops.gn_stats(act.t, act.B, act.H * act.W, act.C, act.stats, workspace=self.workspace)
+        self._op(run)
+
+    def _stats_view(self, a):
+        return a.stats
+
+    def gn_apply(self, xa, xb, ss_fn, eps, adagn, silu, out):
+        """out = act(GN([xa|xb]) * gamma' + beta'); ss_fn(label_idx) -> fp32 tensor slice of 2*C floats."""
+        self.ensure_stats(xa)
+        if xb is not None:
+            self.ensure_stats(xb)
+        C = xa.C + (xb.C if xb is not None else 0)
+        groups = gn_groups(C)
+
+        def run(li):
+            ops.gn_apply(xa.t, xa.C, xb.t if xb is not None else None, xb.C if xb is not None else 0, xa.B,
+                         xa.H * xa.W, self._stats_view(xa), self._stats_view(xb) if xb is not None else None,
+                         groups, eps, ss_fn(li), adagn, silu, out.t)
+        self._op(run)
+
+    def gemm(self, segs, w, out_t, out_mode, out_ld, out_bs=0, bias=None, resid=None, alpha=1.0, bias_fn=None):
+        plan = ops.GemmPlan([(a.t if isinstance(a, Act) else a, taps) for a, taps in segs], w, out_t, out_mode,
+                            out_ld, out_bs, bias=bias, resid=resid.t if isinstance(resid, Act) else resid,
+                            resid_ld=(resid.C if isinstance(resid, Act) else 0), alpha=alpha)
+        self.flops += plan.flops
+        if bias_fn is None:
+            self._op(lambda li: plan.launch())
+        else:
+            self._op(lambda li: plan.launch(bias_fn(li)))
+        return plan
+
+    def fir(self, a, up):
+        H2, W2 = (a.H * 2, a.W * 2) if up else (a.H // 2, a.W // 2)
+        out = self.new_act(H2, W2, a.C)
+        self._op(lambda li: ops.fir_resample(a.t, out.t, a.B, a.H, a.W, a.C, up))
+        return out
+
+    # ----------------------------------------------------------------- execution
+    def finalize(self):
+        self.stats_arena = torch.zeros(max(self.stats_total, 2), dtype=torch.float32, device=self.device)
+        self.workspace = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        for a in self._stat_acts:
+            _, off, n = a.stats
+            a.stats = self.stats_arena[off:off + n]
+
+    def forward(self, label_idx=0):
+        """Enqueue one UNet evaluation: reads self.xin, writes self.eps (B, C_out, H, W) fp32."""
+        for fn in self.ops:
+            fn(label_idx)
+        return self.eps
+
+
+class NCSNppEngine(EngineBase):
+    """Launch plan of NCSNpp.forward (models/better/ncsnpp_more.py:251-392) for batch size B."""
+
+    def __init__(self, net, B, device):
+        cfg = net.config
+        H = cfg.data.image_size
+        super().__init__(device, B, H)
+        self.net = net
+        self.cfg = cfg
+        m, d = cfg.model, cfg.data
+        self.nf = m.ngf
+        self.c_x = d.channels * d.num_frames
+        self.c_cond = d.channels * (d.num_frames_cond + getattr(d, "num_frames_future", 0))
+        self.head_ch = getattr(m, "n_head_channels", -1)
+        if self.nf % 8 != 0:
+            raise EvcError("evcdiff CUDA path needs model.ngf % 8 == 0 (16-byte channel vectors; % 64 for full speed)")
+        if self.c_x + self.c_cond > CIN_PAD:
+            raise EvcError("more than 64 input channels is not supported")
+        sd = {k: v.detach() for k, v in net.state_dict().items()}
+        self.sd = sd
+        self.P = lambda i: f"all_modules.{i}"
+        self._build(sd)
+        self.finalize()
+
+    # ------------------------------------------------------------------ weights
+    def f32(self, key):
+        t = self.sd[key].to(self.device, torch.float32).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _build(self, sd):
+        from .models.better.ncsnpp_more import ncsnpp_spec
+        dev = self.device
+        B, H = self.B, self.H
+        spec = ncsnpp_spec(self.cfg)
+        self.spec = spec
+        P = self.P
+        # --- time-embedding MLP + all AdaGN projections (evaluated per label set, see set_labels)
+        self.temb_w0, self.temb_b0 = self.f32(P(0) + ".weight"), self.f32(P(0) + ".bias")
+        self.temb_w1, self.temb_b1 = self.f32(P(1) + ".weight"), self.f32(P(1) + ".bias")
+        half = self.nf // 2
+        e = math.log(10000) / (half - 1)
+        self.freqs = torch.exp(torch.arange(half, dtype=torch.float32) * -e).to(dev)
+        dw, db, self.ss_off = [], [], {}
+        off = 0
+        for i, s in enumerate(spec):
+            if s["kind"] == "res":
+                for j in (0, 1):
+                    k = f"{P(i)}.actnorm{j}.Dense_0"
+                    dw.append(sd[k + ".weight"].float())
+                    db.append(sd[k + ".bias"].float())
+                    self.ss_off[(i, j)] = (off, dw[-1].shape[0])
+                    off += dw[-1].shape[0]
+        self.dense_w = torch.cat(dw, 0).to(dev).contiguous()
+        self.dense_b = torch.cat(db, 0).to(dev).contiguous()
+        self.ss_total = off
+        self.ss_table = None  # (L, ss_total) fp32, filled by set_labels
+
+        # --- buffers
+        self.xin = torch.zeros((B, H, H, CIN_PAD), dtype=torch.bfloat16, device=dev)
+        self.eps = torch.zeros((B, self.c_x, H, H), dtype=torch.float32, device=dev)
+        xin = Act(self.xin)
+
+        m = self.cfg.model
+        nres, nlev = m.num_res_blocks, len(m.ch_mult)
+        attn_res = list(m.attn_resolutions)
+        i = 2
+        h0 = self.new_act(H, H, spec[i]["cout"], scratch=False)
+        self.gemm([(xin, 9)], pack_conv3(sd[P(i) + ".weight"].to(dev), CIN_PAD), h0.t, EVC_OUT_BF16_ROWS, h0.C,
+                  bias=self.f32(P(i) + ".bias"))
+        self.taps["m2"] = h0
+        i += 1
+        hs = [h0]
+        for lvl in range(nlev):
+            for _ in range(nres):
+                h = self.res_block(i, spec[i], hs[-1], None)
+                i += 1
+                if h.W in attn_res:
+                    h = self.attn_block(i, spec[i], h)
+                    i += 1
+                hs.append(h)
+            if lvl != nlev - 1:
+                hs.append(self.res_block(i, spec[i], hs[-1], None))
+                i += 1
+        h = hs[-1]
+        h = self.res_block(i, spec[i], h, None); i += 1
+        h = self.attn_block(i, spec[i], h); i += 1
+        h = self.res_block(i, spec[i], h, None); i += 1
+        for lvl in reversed(range(nlev)):
+            for _ in range(nres + 1):
+                h = self.res_block(i, spec[i], h, hs.pop())
+                i += 1
+            if h.W in attn_res:
+                h = self.attn_block(i, spec[i], h)
+                i += 1
+            if lvl != 0:
+                h = self.res_block(i, spec[i], h, None)
+                i += 1
+        assert not hs
+        # final GroupNorm(affine)+SiLU and conv3x3 -> NCHW fp32 eps
+        ss = torch.cat([sd[P(i) + ".Norm_0.weight"].float(), sd[P(i) + ".Norm_0.bias"].float()]).to(dev).contiguous()
+        self._keep.append(ss)
+        hn = self.new_act(h.H, h.W, h.C)
+        self.gn_apply(h, None, lambda li: ss, 1e-5, False, True, hn)
+        self.taps[f"m{i}"] = hn
+        i += 1
+        self.gemm([(hn, 9)], pack_conv3(sd[P(i) + ".weight"].to(dev)), self.eps, EVC_OUT_F32_T, H * H,
+                  out_bs=self.c_x * H * H, bias=self.f32(P(i) + ".bias"))
+        i += 1
+        assert i == len(spec)
+
+    # ------------------------------------------------------------------ blocks
+    def _ss(self, i, j):
+        off, n = self.ss_off[(i, j)]
+        return lambda li: self.ss_table[li, off:off + n]
+
+    def res_block(self, i, s, xa, xb):
+        """ResnetBlockBigGANppGN (layerspp.py:595-624) on the virtual concat [xa | xb]."""
+        sd, P, dev = self.sd, self.P, self.device
+        cin, cout = s["cin"], s["cout"]
+        assert cin == xa.C + (xb.C if xb is not None else 0)
+        h = self.new_act(xa.H, xa.W, cin)
+        self.gn_apply(xa, xb, self._ss(i, 0), 1e-5, True, True, h)
+        xs = [xa] + ([xb] if xb is not None else [])
+        tmp = []
+        if s["up"] or s["down"]:
+            h2 = self.fir(h, s["up"])
+            self.release(h)
+            h = h2
+            xs = [self.fir(x, s["up"]) for x in xs]
+            tmp += xs
+        c0 = self.new_act(h.H, h.W, cout)
+        self.gemm([(h, 9)], pack_conv3(sd[P(i) + ".Conv_0.weight"].to(dev)), c0.t, EVC_OUT_BF16_ROWS, cout,
+                  bias=self.f32(P(i) + ".Conv_0.bias"))
+        self.release(h)
+        a1 = self.new_act(c0.H, c0.W, cout)
+        self.gn_apply(c0, None, self._ss(i, 1), 1e-5, True, True, a1)
+        out = self.new_act(c0.H, c0.W, cout, scratch=False)
+        w1 = pack_conv3(sd[P(i) + ".Conv_1.weight"].to(dev))
+        b1 = sd[P(i) + ".Conv_1.bias"].float()
+        if (P(i) + ".Conv_2.weight") in sd:
+            w2 = sd[P(i) + ".Conv_2.weight"].to(dev).reshape(cout, cin).to(torch.bfloat16)
+            w = torch.cat([w1, w2], dim=1).contiguous()
+            bias = (b1 + sd[P(i) + ".Conv_2.bias"].float()).to(dev).contiguous()
+            self._keep.append(bias)
+            self.gemm([(a1, 9)] + [(x, 1) for x in xs], w, out.t, EVC_OUT_BF16_ROWS, cout, bias=bias, alpha=RSQRT2)
+        else:
+            assert len(xs) == 1 and xs[0].C == cout
+            bias = b1.to(dev).contiguous()
+            self._keep.append(bias)
+            self.gemm([(a1, 9)], w1, out.t, EVC_OUT_BF16_ROWS, cout, bias=bias, resid=xs[0], alpha=RSQRT2)
+        self.release(c0, a1, *tmp)
+        self.taps[f"m{i}"] = out
+        return out
+
+    def attn_block(self, i, s, x):
+        """AttnBlockpp (layerspp.py:230-249): GN(affine, eps 1e-6) -> q,k,v NIN -> softmax(q k^T / sqrt(d)) v -> NIN_3."""
+        sd, P, dev = self.sd, self.P, self.device
+        C, N, B = x.C, x.H * x.W, self.B
+        heads = 1 if (self.head_ch == -1 or C < self.head_ch) else C // self.head_ch
+        d = C // heads
+        if d % 8 != 0:
+            raise EvcError("attention head dim must be a multiple of 8")
+        ss = torch.cat([sd[P(i) + ".GroupNorm_0.weight"].float(), sd[P(i) + ".GroupNorm_0.bias"].float()]).to(dev)
+        ss = ss.contiguous()
+        self._keep.append(ss)
+        hn = self.new_act(x.H, x.W, C)
+        self.gn_apply(x, None, lambda li: ss, 1e-6, False, False, hn)
+        # NIN: y = x @ W + b with W (in, out) -> GEMM weight rows = outputs
+        wq, wk, wv, wo = [sd[P(i) + f".NIN_{j}.W"].to(dev).t().to(torch.bfloat16) for j in range(4)]
+        bq, bk, bv, bo = [sd[P(i) + f".NIN_{j}.b"].float().to(dev) for j in range(4)]
+        qk = self.pool.get((B, x.H, x.W, 2 * C))
+        self.gemm([(hn, 1)], torch.cat([wq, wk], 0).contiguous(), qk, EVC_OUT_BF16_ROWS, 2 * C,
+                  bias=torch.cat([bq, bk]).contiguous())
+        # key axis padded to a multiple of 8 (16-byte TMA strides); only toy shapes (N < 8) ever pad.  Pad columns:
+        # S = -inf (never written by the GEMM, so softmax gives P = 0) and V^T = 0.
+        Np = max(8, (N + 7) // 8 * 8)
+        if Np == N:
+            vT = self.pool.get((B, C, N))
+            S = self.pool.get((B, N, N), torch.float32)
+            Pm = self.pool.get((B, N, N))
+        else:
+            vT = torch.zeros((B, C, Np), dtype=torch.bfloat16, device=dev)
+            S = torch.full((B, N, Np), float("-inf"), dtype=torch.float32, device=dev)
+            Pm = torch.zeros((B, N, Np), dtype=torch.bfloat16, device=dev)
+        self.gemm([(hn, 1)], wv.contiguous(), vT, EVC_OUT_BF16_T, Np, out_bs=C * Np, bias=bv.contiguous())
+        o = self.new_act(x.H, x.W, C)
+        qk3 = qk.view(B, N, 2 * C)
+        o3 = o.t.view(B, N, C)
+        for hd in range(heads):
+            q = qk3[:, :, hd * d:(hd + 1) * d].unsqueeze(1)  # (B,1,N,d)
+            k = qk3[:, :, C + hd * d:C + (hd + 1) * d]  # (B,N,d)  per-sample B operand
+            self.gemm([(q, 1)], k, S, EVC_OUT_F32_ROWS, Np, alpha=float(int(d) ** (-0.5)))
+            self._op(lambda li, S=S, Pm=Pm: ops.softmax_rows(S, Pm, B * N, Np))
+            self.gemm([(Pm.view(B, 1, N, Np), 1)], vT[:, hd * d:(hd + 1) * d, :], o3[:, :, hd * d:], EVC_OUT_BF16_ROWS, C)
+        out = self.new_act(x.H, x.W, C, scratch=False)
+        self.gemm([(o, 1)], wo.contiguous(), out.t, EVC_OUT_BF16_ROWS, C, bias=bo.contiguous(), resid=x, alpha=RSQRT2)
+        self.pool.put(qk)
+        if Np == N:
+            self.pool.put(vT); self.pool.put(S); self.pool.put(Pm)
+        else:
+            self._keep += [vT, S, Pm]
+        self.release(hn, o)
+        self.taps[f"m{i}"] = out
+        return out
+
+    # ------------------------------------------------------------------ per-label tables
+    def set_labels(self, labels):
+        """labels: iterable of floats (the distinct `y` values the sampler will use, in order).  Evaluates
+        get_timestep_embedding + the temb MLP + every Dense_0(SiLU(temb)) once per label (layers.py:504-518,
+        ncsnpp_more.py:277-281, layerspp.py:520-522)."""
+        lab = torch.tensor([float(v) for v in labels], dtype=torch.float32, device=self.device)
+        L = lab.numel()
+        emb = torch.empty((L, self.nf), dtype=torch.float32, device=self.device)
+        ops.timestep_embedding(lab, self.freqs, self.nf, emb)
+        t1 = torch.empty((L, 4 * self.nf), dtype=torch.float32, device=self.device)
+        ops.linear_f32(emb, self.temb_w0, self.temb_b0, t1)
+        t2 = torch.empty_like(t1)
+        ops.linear_f32(t1, self.temb_w1, self.temb_b1, t2, act_in=True)
+        if self.ss_table is None or self.ss_table.shape[0] < L:
+            self.ss_table = torch.empty((L, self.ss_total), dtype=torch.float32, device=self.device)
+        ops.linear_f32(t2, self.dense_w, self.dense_b, self.ss_table[:L], act_in=True)
+        self.labels = [float(v) for v in labels]
+        self.temb = t2
+        return L
+
+    def load_input(self, x, cond):
+        """x (B,15,H,W) fp32, cond (B,6,H,W) fp32/fp64 or None -> NHWC bf16 UNet input (torch.cat of
+        ncsnpp_more.py:256-257 + the fp32 cast of :293, fused with the layout change)."""
+        ops.pack_nchw(x.contiguous(), self.xin, 0)
+        if cond is not None:
+            ops.pack_nchw(cond.contiguous(), self.xin, self.c_x)

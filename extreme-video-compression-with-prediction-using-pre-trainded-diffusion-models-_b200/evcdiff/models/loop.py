@@ -1,0 +1,199 @@
+"""The multi-step sampling loop on one GPU: static state buffers, kernel enqueue order, CUDA-graph capture.
+
+One SamplerLoop per (model, batch size, device).  It owns
+  x      (B,15,H,W) fp32   sampler state, the layout the reference samplers return
+  noise  (B,15,H,W) fp32   filled by `normal_()` from the global CUDA generator (same draw as torch.randn_like)
+  e[j]   (B,15,H,W) fp32   eps history / Runge-Kutta stages for F-PNDM
+and the UNet engine (evcdiff.engine) whose `xin` (NHWC bf16) every update kernel refreshes in place.
+A whole loop (e.g. 101 UNet evaluations + 101 updates + 99 noise draws for DDPM-100) is captured once into a
+single CUDA graph per key and replayed; inputs are copied into the static buffers before the replay.
+"""
+import torch
+
+from .. import ops
+from .._lib import EvcError, PndmCoef
+
+
+class SamplerLoop:
+    @staticmethod
+    def get(net, B, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise EvcError("evcdiff samplers need CUDA tensors (no CPU fallback)")
+        eng = net.engine(B, device)
+        loop = getattr(eng, "_loop", None)
+        if loop is None:
+            loop = SamplerLoop(net, eng)
+            eng._loop = loop
+        return loop
+
+    def __init__(self, net, eng):
+        self.net, self.eng = net, eng
+        dev = eng.device
+        shape = tuple(eng.eps.shape)
+        self.x = torch.zeros(shape, dtype=torch.float32, device=dev)
+        self.noise = torch.zeros(shape, dtype=torch.float32, device=dev)
+        self.e = None
+        self.scratch = None
+        self.graphs = {}
+        self.launches_per_run = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _load(self, x_mod, cond):
+        if tuple(x_mod.shape) != tuple(self.x.shape):
+            raise EvcError(f"x_mod shape {tuple(x_mod.shape)} does not match the model ({tuple(self.x.shape)})")
+        self.x.copy_(x_mod.to(torch.float32))
+        self.eng.xin.zero_()
+        self.eng.load_input(self.x, cond)
+
+    def _capture_or_run(self, key, body, graph):
+        """body() enqueues the loop on the current stream.  With graph=True it is captured once and replayed."""
+        if not graph:
+            n0 = ops.launch_count()
+            body()
+            self.launches_per_run[key] = ops.launch_count() - n0
+            return
+        g = self.graphs.get(key)
+        if g is None:
+            # warm-up run on a side stream (module loading, cudaFuncSetAttribute, lazy allocations) --
+            # capture must not be the first execution.  The state is restored afterwards.
+            x0, xin0 = self.x.clone(), self.eng.xin.clone()
+            rng = torch.cuda.get_rng_state(self.eng.device)
+            s = torch.cuda.Stream(device=self.eng.device)
+            s.wait_stream(torch.cuda.current_stream(self.eng.device))
+            with torch.cuda.stream(s):
+                self.eng.forward(0)
+                self._warm_updates()
+            torch.cuda.current_stream(self.eng.device).wait_stream(s)
+            torch.cuda.synchronize(self.eng.device)
+            self.x.copy_(x0)
+            self.eng.xin.copy_(xin0)
+            torch.cuda.set_rng_state(rng, self.eng.device)
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                body()
+            self.launches_per_run[key] = ops.launch_count() - n0
+            self.graphs[key] = g
+            # capture does not execute: restore state (nothing ran) and replay below
+        g.replay()
+
+    def _warm_updates(self):
+        """First execution of the update kernels / RNG kernel outside capture (results discarded)."""
+        from .._lib import StepCoef
+        if self.scratch is None:
+            self.scratch = torch.zeros_like(self.x)
+        self.noise.normal_()
+        ops.sampler_update(self.x, self.eng.eps, self.noise, self.scratch, None, StepCoef(0, 1, 1.0, 0.5, 0.5, 0.5, 0.0, 0.1))
+        c = PndmCoef()
+        c.n_e, c.clip, c.w_scale, c.d, c.p, c.q = 1, 1, 1.0, 0.1, 0.1, 0.1
+        c.w[0] = 1.0
+        ops.pndm_update(self.x, [self.eng.eps], self.scratch, None, None, c)
+        self.scratch.copy_(self.eng.eps)
+
+    # ------------------------------------------------------------------------------------------
+    def run_ancestral(self, key, x_mod, cond, labels, coefs, final_only, noise=None, noise_const=None, graph=True):
+        eng = self.eng
+        uniq = list(dict.fromkeys(labels))
+        idx = [uniq.index(v) for v in labels]
+        eng.set_labels(uniq)
+        self._load(x_mod, cond)
+        images = []
+        ext_noise = noise is not None or noise_const is not None
+        if ext_noise or not final_only:
+            graph = False  # per-step host interaction: eager launches
+
+        def body():
+            ni = 0
+            for i, c in enumerate(coefs):
+                eng.forward(idx[i])
+                nz = None
+                if c.mode == 0 and c.c_noise != 0.0:
+                    if noise_const is not None:
+                        nz = noise_const
+                    elif noise is not None:
+                        nz = noise[ni].to(self.x.device, torch.float32).contiguous()
+                        ni += 1
+                    else:
+                        self.noise.normal_()
+                        nz = self.noise
+                ops.sampler_update(self.x, eng.eps, nz, self.x, eng.xin, c)
+                if not final_only:
+                    images.append(self.x.to("cpu"))
+
+        self._capture_or_run(key + (len(uniq), eng.ss_table.data_ptr()), body, graph)
+        if final_only:
+            return self.x.clone().unsqueeze(0)
+        return torch.stack(images)
+
+    # ------------------------------------------------------------------------------------------
+    def run_fpndm(self, key, x_mod, cond, steps, steps_next, alphas_old, clip_before, final_only, graph=True):
+        """F-PNDM (reference models/__init__.py:79-100 + models/pndm.py:3-52)."""
+        eng = self.eng
+        if self.e is None:
+            self.e = [torch.zeros_like(self.x) for _ in range(7)]  # ring of 4 + 3 Runge-Kutta stages
+            self.scratch = torch.zeros_like(self.x)
+        # label sequence exactly as the network sees it: t.long() values and the float midpoints
+        plan = []  # (kind, t, t_next)
+        n_ets = 0
+        for t, tn in zip(steps, steps_next):
+            plan.append(("ab" if n_ets > 2 else "rk", float(t), float(tn)))
+            n_ets += 1
+        labs = []
+        for kind, t, tn in plan:
+            labs += [t] if kind == "ab" else [t, (t + tn) / 2, (t + tn) / 2, tn]
+        uniq = list(dict.fromkeys(labs))
+        eng.set_labels(uniq)
+        li = {v: uniq.index(v) for v in uniq}
+        self._load(x_mod, cond)
+        images = []
+        if not final_only:
+            graph = False
+
+        def coef(t, tn, n_e, w, w_scale):
+            at = alphas_old[int(torch.tensor(t).long()) + 1]
+            an = alphas_old[int(torch.tensor(tn).long()) + 1]
+            d = an - at
+            p = 1 / (at.sqrt() * (at.sqrt() + an.sqrt()))
+            q = 1 / (at.sqrt() * (((1 - an) * at).sqrt() + ((1 - at) * an).sqrt()))
+            c = PndmCoef()
+            c.n_e, c.clip = n_e, int(bool(clip_before))
+            for j in range(4):
+                c.w[j] = float(w[j]) if j < n_e else 0.0
+            c.w_scale = float(torch.tensor(w_scale, dtype=torch.float32))
+            c.d, c.p, c.q = float(d), float(p), float(q)
+            return c
+
+        def body():
+            ring = []  # eps history buffers, most recent last
+            free = list(self.e)
+            for kind, t, tn in plan:
+                if len(ring) == 4:
+                    free.append(ring.pop(0))
+                e1 = free.pop()
+                if kind == "ab":
+                    eng.forward(li[t])
+                    e1.copy_(eng.eps)
+                    ring.append(e1)
+                    es = [ring[-1], ring[-2], ring[-3], ring[-4]]
+                    ops.pndm_update(self.x, es, self.x, None, eng.xin, coef(t, tn, 4, (55.0, -59.0, 37.0, -9.0), 1 / 24))
+                else:
+                    tm = (t + tn) / 2
+                    e2, e3, e4 = free[-1], free[-2], free[-3]
+                    eng.forward(li[t]); e1.copy_(eng.eps)
+                    ring.append(e1)
+                    ops.pndm_update(self.x, [e1], self.scratch, None, eng.xin, coef(t, tm, 1, (1.0,), 1.0))
+                    eng.forward(li[tm]); e2.copy_(eng.eps)
+                    ops.pndm_update(self.x, [e2], self.scratch, None, eng.xin, coef(t, tm, 1, (1.0,), 1.0))
+                    eng.forward(li[tm]); e3.copy_(eng.eps)
+                    ops.pndm_update(self.x, [e3], self.scratch, None, eng.xin, coef(t, tn, 1, (1.0,), 1.0))
+                    eng.forward(li[tn]); e4.copy_(eng.eps)
+                    ops.pndm_update(self.x, [e1, e2, e3, e4], self.x, None, eng.xin,
+                                    coef(t, tn, 4, (1.0, 2.0, 2.0, 1.0), 1 / 6))
+                if not final_only:
+                    images.append(self.x.to("cpu"))
+
+        self._capture_or_run(key + (len(uniq), eng.ss_table.data_ptr()), body, graph)
+        if final_only:
+            return self.x.clone().unsqueeze(0)
+        return torch.stack(images)

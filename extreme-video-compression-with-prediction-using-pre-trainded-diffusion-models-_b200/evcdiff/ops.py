@@ -93,10 +93,32 @@ def pick_bn(n):
     return min(256, ((n + 15) // 16) * 16)
 
 
-def gn_stats(x, B, HW, C, stats, ldx=None):
-    """stats (B,C,2) fp32 += per-channel [sum, sumsq] of x (B*HW rows of C bf16)."""
+def gn_stats_workspace_bytes(B, HW, Cc):
+    n = C.c_int64(0)
+    check(load().evc_gn_stats_workspace(B, HW, Cc, C.byref(n)), "evc_gn_stats_workspace")
+    return int(n.value)
+
+
+_ws_cache = {}
+
+
+def _default_workspace(device, nbytes):
+    key = str(device)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def gn_stats(x, B, HW, C, stats, ldx=None, workspace=None):
+    """stats (B,C,2) fp32 = per-channel [sum, sumsq] of x (B*HW rows of C bf16).  workspace: zero-initialised
+    uint8 scratch (shared between calls on one stream); a per-device default is used when omitted."""
     _require_cuda(x, stats)
-    check(load().evc_gn_stats(_ptr(x), ldx or C, B, HW, C, _ptr(stats), C, 0, stream_ptr()), "evc_gn_stats")
+    if workspace is None:
+        workspace = _default_workspace(x.device, gn_stats_workspace_bytes(B, HW, C))
+    check(load().evc_gn_stats(_ptr(x), ldx or C, B, HW, C, _ptr(stats), C, 0, _ptr(workspace), workspace.numel(),
+                              stream_ptr()), "evc_gn_stats")
 
 
 def gn_apply(x0, C0, x1, C1, B, HW, stats0, stats1, groups, eps, ss, adagn, silu, y):

@@ -50,7 +50,7 @@ int64_t evc_launch_count(void);
  *                               + bias[n] + resid[b, y, x, n] )
  *
  * A segments: up to 3 bf16 tensors viewed as (B, H, W, C) with element strides; taps = 1 (1x1 / GEMM)
- * or 9 (3x3, zero padding 1).  C must be a multiple of 64.  Several segments implement a virtual
+ * or 9 (3x3, zero padding 1).  C must be a multiple of 8 (64 for full tensor-core efficiency).  Several segments implement a virtual
  * channel concat and the fused 1x1 skip branch of a residual block (extra K).
  * Wt: bf16 (w_batches, N, K_total), K contiguous, K order = segment-major, tap-major, channel-minor.
  * w_batches is 1 (shared weights) or B (per-sample B operand, e.g. K / V^T in attention; then the
@@ -104,10 +104,13 @@ double evc_gemm_plan_flops(const evc_gemm_plan* plan);
  * GroupNorm statistics and the fused normalise / AdaGN / affine / SiLU pass.
  * Replaces nn.GroupNorm + get_act_norm (layerspp.py:465-549) and Normalize+Swish (unet.py:44-46,90-95).
  * ---------------------------------------------------------------------------------------------- */
-/* stats[(b*c_total + c_off + c)*2 + {0,1}] += {sum, sum of squares} over the HW pixels of x (bf16 rows,
- * row stride ldx).  stats must be zeroed by the caller (evc_fill_zero). C % 8 == 0. */
+/* stats[(b*c_total + c_off + c)*2 + {0,1}] = {sum, sum of squares} over the HW pixels of x (bf16 rows, row stride
+ * ldx), C % 8 == 0.  Deterministic (no floating-point atomics).  `workspace` is caller-owned scratch of at least
+ * evc_gn_stats_workspace() bytes whose first bytes (the ticket counters) must be zero before the FIRST use; the
+ * kernel leaves them zero, so one workspace can be shared by every call on the same stream. */
+int evc_gn_stats_workspace(int32_t B, int32_t HW, int32_t C, int64_t* bytes);
 int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, float* stats, int32_t c_total,
-                 int32_t c_off, evc_stream_t stream);
+                 int32_t c_off, void* workspace, int64_t workspace_bytes, evc_stream_t stream);
 
 /* y[b, p, c] = act( (x[b,p,c] - mean_g) * rstd_g * (gamma'[c]) + beta'[c] ), group g = c / (C/groups) over the
  * concatenation [x0 | x1] (x1 may be NULL).  mean/rstd come from the per-channel sums `stats0` (B,C0,2) and

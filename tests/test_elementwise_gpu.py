@@ -1,0 +1,181 @@
+"""GPU parity of the HBM-bound kernels (GroupNorm stats/apply, FIR, softmax, pack, sampler updates, temb)
+against the oracle / plain torch fp32.  bf16 outputs: rel-L2 <= 4e-3 (one rounding); fp32 outputs <= 1e-6."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import common
+from oracle import ncsnpp as O
+from oracle import samplers as S
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ops():
+    from evcdiff import ops
+    return ops
+
+
+def nhwc(x):  # NCHW fp32 -> NHWC bf16
+    return x.permute(0, 2, 3, 1).contiguous().bfloat16()
+
+
+def nchw(x):  # NHWC bf16 -> NCHW fp32
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("B,H,C0,C1,adagn,silu,eps", [
+    (2, 16, 192, 0, True, True, 1e-5), (3, 8, 768, 576, True, True, 1e-5), (2, 32, 384, 192, True, True, 1e-5),
+    (2, 16, 576, 0, False, False, 1e-6), (1, 128, 192, 0, False, True, 1e-5), (2, 4, 64, 32, True, True, 1e-5),
+])
+def test_groupnorm(B, H, C0, C1, adagn, silu, eps):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(1)
+    C = C0 + C1
+    x0 = nhwc(torch.randn(B, C0, H, H, device=DEV, generator=g) * 1.7 + 0.3)
+    x1 = nhwc(torch.randn(B, C1, H, H, device=DEV, generator=g) * 0.6 - 0.2) if C1 else None
+    ss = torch.randn(2 * C, device=DEV, generator=g) * 0.3
+    if not adagn:
+        ss[:C] += 1.0
+    st0 = torch.zeros(B, C0, 2, device=DEV)
+    ops.gn_stats(x0, B, H * H, C0, st0)
+    st1 = None
+    if C1:
+        st1 = torch.zeros(B, C1, 2, device=DEV)
+        ops.gn_stats(x1, B, H * H, C1, st1)
+    y = torch.empty(B, H, H, C, device=DEV, dtype=torch.bfloat16)
+    groups = O.gn_groups(C)
+    ops.gn_apply(x0, C0, x1, C1, B, H * H, st0, st1, groups, eps, ss, adagn, silu, y)
+    torch.cuda.synchronize()
+    xc = torch.cat([nchw(x0)] + ([nchw(x1)] if C1 else []), 1)
+    ref_sum = xc.sum((2, 3))
+    assert common.rel_l2(st0[..., 0], ref_sum[:, :C0]) < 1e-5
+    h = F.group_norm(xc, groups, None, None, eps=eps)
+    gam = (1 + ss[:C]) if adagn else ss[:C]
+    h = h * gam.view(1, C, 1, 1) + ss[C:].view(1, C, 1, 1)
+    if silu:
+        h = F.silu(h)
+    assert common.rel_l2(nchw(y), h) < 4e-3
+
+
+@pytest.mark.parametrize("B,H,C", [(2, 8, 192), (1, 64, 192), (3, 16, 576), (2, 4, 64)])
+def test_fir(B, H, C):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(2)
+    x = nhwc(torch.randn(B, C, H, H, device=DEV, generator=g))
+    up = torch.empty(B, 2 * H, 2 * H, C, device=DEV, dtype=torch.bfloat16)
+    dn = torch.empty(B, H // 2, H // 2, C, device=DEV, dtype=torch.bfloat16)
+    ops.fir_resample(x, up, B, H, H, C, True)
+    ops.fir_resample(x, dn, B, H, H, C, False)
+    torch.cuda.synchronize()
+    assert common.rel_l2(nchw(up), O.fir_up2(nchw(x))) < 4e-3
+    assert common.rel_l2(nchw(dn), O.fir_down2(nchw(x))) < 4e-3
+
+
+def test_nearest_up():
+    ops = _ops()
+    x = nhwc(torch.randn(2, 64, 8, 8, device=DEV))
+    y = torch.empty(2, 16, 16, 64, device=DEV, dtype=torch.bfloat16)
+    ops.nearest_up2(x, y, 2, 8, 8, 64)
+    torch.cuda.synchronize()
+    assert torch.equal(nchw(y), F.interpolate(nchw(x), scale_factor=2, mode="nearest"))
+
+
+@pytest.mark.parametrize("rows,cols", [(64, 64), (1000, 256), (2048, 1024), (512, 4096), (32, 16), (8, 4)])
+def test_softmax(rows, cols):
+    ops = _ops()
+    s = torch.randn(rows, cols, device=DEV) * 4
+    p = torch.empty(rows, cols, device=DEV, dtype=torch.bfloat16)
+    ops.softmax_rows(s, p, rows, cols)
+    torch.cuda.synchronize()
+    assert common.rel_l2(p.float(), F.softmax(s, -1)) < 4e-3
+
+
+def test_pack_and_inverse():
+    ops = _ops()
+    x = torch.randn(3, 15, 16, 16, device=DEV)
+    c = torch.rand(3, 6, 16, 16, device=DEV, dtype=torch.float64)
+    dst = torch.zeros(3, 16, 16, 64, device=DEV, dtype=torch.bfloat16)
+    ops.pack_nchw(x, dst, 0)
+    ops.pack_nchw(c, dst, 15, scale=2.0, shift=-1.0)
+    torch.cuda.synchronize()
+    ref = torch.cat([x, (2 * c - 1).float()], 1).bfloat16().float()
+    assert torch.equal(nchw(dst)[:, :21], ref)
+    assert float(nchw(dst)[:, 21:].abs().max()) == 0.0
+    fr = torch.empty_like(x)
+    ops.inverse_transform(x, fr)
+    assert common.rel_l2(fr, torch.clamp((x + 1) / 2, 0, 1)) < 1e-7
+
+
+def test_temb_and_linear():
+    ops = _ops()
+    t = torch.tensor([0.0, 10.0, 990.0, 999.0, -0.5, 25.0, -1.0], device=DEV)
+    from evcdiff.models.better.layers import get_timestep_embedding
+    e = get_timestep_embedding(t, 192)
+    ref = O.timestep_embedding(t, 192)
+    assert float((e - ref).abs().max()) < 2e-5  # sinf/cosf of arguments up to ~1e3 in fp32
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(29, 768, device=DEV, generator=g)
+    W = torch.randn(1000, 768, device=DEV, generator=g) / 28
+    b = torch.randn(1000, device=DEV, generator=g)
+    y = torch.empty(29, 1000, device=DEV)
+    ops.linear_f32(x, W, b, y, act_in=True)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = F.linear(F.silu(x).double(), W.double(), b.double()).float()
+    assert common.rel_l2(y, ref) < 1e-6
+
+
+def test_sampler_updates_match_oracle_arithmetic():
+    """DDPM / DDIM / denoise / PNDM transfer updates against the oracle's tensor expressions (fp32, CUDA)."""
+    ops = _ops()
+    from evcdiff._lib import PndmCoef, StepCoef
+    cfg = common.tiny_config(device=DEV)
+    betas, alphas, alphas_prev = S.schedule(cfg, DEV)
+    steps, a, ap, b = S._subsample(alphas, alphas_prev, betas, 100)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    x = torch.randn(2, 15, 16, 16, device=DEV, generator=g)
+    e = torch.randn(2, 15, 16, 16, device=DEV, generator=g)
+    nz = torch.randn(2, 15, 16, 16, device=DEV, generator=g)
+    xin = torch.zeros(2, 16, 16, 64, device=DEV, dtype=torch.bfloat16)
+    for i in (0, 37, 98):
+        ca, cap, cb = a[i], ap[i], b[i]
+        x0 = ((1 / ca.sqrt()) * (x - (1 - ca).sqrt() * e)).clip_(-1, 1)
+        ref = (cap.sqrt() * cb / (1 - ca)) * x0 + ((1 - cb).sqrt() * (1 - cap) / (1 - ca)) * x
+        ref = ref + ((1 - cap) / (1 - ca) * cb).sqrt() * nz
+        c = StepCoef(0, 1, float(1 / ca.sqrt()), float((1 - ca).sqrt()), float(cap.sqrt() * cb / (1 - ca)),
+                     float((1 - cb).sqrt() * (1 - cap) / (1 - ca)), 0.0, float(((1 - cap) / (1 - ca) * cb).sqrt()))
+        out = torch.empty_like(x)
+        ops.sampler_update(x, e, nz, out, xin, c)
+        torch.cuda.synchronize()
+        assert common.rel_l2(out, ref) < 1e-6
+        assert torch.equal(nchw(xin)[:, :15], out.bfloat16().float())
+        # DDIM
+        ref = cap.sqrt() * x0 + (1 - cap).sqrt() * e
+        c = StepCoef(0, 1, float(1 / ca.sqrt()), float((1 - ca).sqrt()), float(cap.sqrt()), 0.0, float((1 - cap).sqrt()), 0.0)
+        ops.sampler_update(x, e, None, out, None, c)
+        torch.cuda.synchronize()
+        assert common.rel_l2(out, ref) < 1e-6
+    ref = x - (1 - a[-1]).sqrt() * e
+    ops.sampler_update(x, e, None, out, None, StepCoef(1, 0, 0.0, float((1 - a[-1]).sqrt()), 0, 0, 0, 0))
+    torch.cuda.synchronize()
+    assert common.rel_l2(out, ref) < 1e-7
+    # PNDM transfer + linear multistep through the public pndm mirror
+    from evcdiff.models import pndm
+    a_old = alphas.flip(0)
+    for (t, tn) in [(50.0, 25.0), (0.0, -0.5), (950.0, 900.0)]:
+        tt = torch.full((2,), t, device=DEV)
+        tnn = torch.full((2,), tn, device=DEV)
+        for clip in (True, False):
+            ref = S.transfer(x, tt, tnn, e, a_old, clip_before=clip)
+            got = pndm.transfer(x, tt, tnn, e, a_old, clip_before=clip)
+            torch.cuda.synchronize()
+            assert common.rel_l2(got, ref) < 1e-6
+    es = [torch.randn_like(x) for _ in range(4)]
+    ref = (1 / 24) * (55 * es[0] - 59 * es[1] + 37 * es[2] - 9 * es[3])
+    got = pndm._combine(es, (55.0, -59.0, 37.0, -9.0), 1 / 24)
+    torch.cuda.synchronize()
+    assert common.rel_l2(got, ref) < 1e-6

@@ -1,0 +1,111 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the model mirrors the
+reference's state dict, unsupported configurations and CPU tensors fail loudly (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import common
+from oracle import ncsnpp as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from evcdiff import _lib
+    hdr = open(os.path.join(ROOT, "include", "evcdiff.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(evc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.evc_version() >= 1
+    assert lib.evc_launch_count() == 0 or lib.evc_launch_count() > 0
+
+
+def test_invalid_arguments_are_errors_not_fallbacks():
+    from evcdiff import _lib
+    lib = _lib.load()
+    d = _lib.GemmDesc()
+    h = ctypes.c_void_p()
+    assert lib.evc_gemm_plan_create(ctypes.byref(d), ctypes.byref(h)) == -1
+    assert b"n_seg" in lib.evc_last_error()
+    assert lib.evc_gn_stats(None, 8, 1, 1, 8, None, 8, 0, None, 0, None) == -1
+    assert lib.evc_softmax_rows(None, None, 1, 3, None) == -1
+
+
+def test_state_dict_matches_reference_layout():
+    from evcdiff.models.better.ncsnpp_more import UNetMore_DDPM, ncsnpp_spec
+    for cfgf in (common.tiny_config, common.gpu64_config):
+        cfg = cfgf()
+        net = UNetMore_DDPM(cfg)
+        sd = net.state_dict()
+        shapes = O.ncsnpp_param_shapes(cfg)
+        keys = [k for k in sd if k not in ("betas", "alphas", "alphas_prev", "unet.sigmas")]
+        assert keys == list(shapes.keys())
+        assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in keys)
+        assert ncsnpp_spec(cfg) == [{**s, **({"init_scale": 1.0} if i == 2 else {}),
+                                     **({"init_scale": 0.0} if i == len(O.ncsnpp_spec(cfg)) - 1 else {})}
+                                    for i, s in enumerate(O.ncsnpp_spec(cfg))]
+        # schedule buffers: index 0 = noisiest
+        assert torch.equal(net.alphas_prev[:-1], net.alphas[1:]) and float(net.alphas_prev[-1]) == 1.0
+        assert float(net.alphas[0]) < 1e-4 and float(net.alphas[-1]) > 0.999
+        # zero-init layers of the reference (Conv_1, NIN_3, output conv)
+        assert float(sd["unet.all_modules.3.Conv_1.weight"].abs().max()) < 1e-4
+        # DataParallel-style checkpoints load after stripping the `module.` prefix (city_sender.py:313-322)
+        dp = {"module." + k: v for k, v in sd.items()}
+        net2 = UNetMore_DDPM(cfg)
+        net2.load_state_dict({k[len("module."):]: v for k, v in dp.items()}, strict=True)
+
+
+def test_no_cpu_fallback():
+    from evcdiff import models as M
+    from evcdiff._lib import EvcError
+    from evcdiff.models.better.ncsnpp_more import UNetMore_DDPM
+    cfg = common.tiny_config()
+    net = UNetMore_DDPM(cfg)
+    x = torch.randn(1, 15, 16, 16)
+    with pytest.raises(EvcError):
+        net(x, torch.zeros(1, dtype=torch.long), cond=torch.zeros(1, 6, 16, 16))
+    with pytest.raises(EvcError):
+        M.ddpm_sampler(x, net, cond=None, subsample_steps=10)
+    with pytest.raises(EvcError):
+        M.ddpm_sampler(x, torch.nn.Identity(), subsample_steps=10)
+    with pytest.raises(EvcError):
+        M.ddpm_sampler(x, net, gamma=True)
+    with pytest.raises(EvcError):
+        M.ddim_sampler(x, net, t_min=0.5)
+    with pytest.raises(TypeError):
+        M.FPNDM_sampler(x, net, subsample_steps=None)  # reference models/__init__.py:62 crashes the same way
+
+
+def test_unsupported_configs_raise():
+    from evcdiff._lib import EvcError
+    from evcdiff.models.better.ncsnpp_more import UNetMore_DDPM
+    for key in ("spade", "cond_emb", "noise_in_cond", "gamma"):
+        cfg = common.tiny_config()
+        setattr(cfg.model, key, True)
+        with pytest.raises(EvcError):
+            UNetMore_DDPM(cfg)
+    cfg = common.tiny_config()
+    cfg.model.arch = "unetmore3d"
+    with pytest.raises(EvcError):
+        UNetMore_DDPM(cfg)
+
+
+def test_get_sigmas_and_coefficients():
+    from evcdiff import models as M
+    from evcdiff.models.better.ncsnpp_more import UNetMore_DDPM
+    from oracle import samplers as S
+    cfg = common.tiny_config()
+    assert torch.equal(M.get_sigmas(cfg), S.schedule(cfg)[0])
+    net = UNetMore_DDPM(cfg)
+    steps, a, ap, b = M._subsampled_schedule(net, 100)
+    s2, a2, ap2, b2 = S._subsample(net.alphas, net.alphas_prev, net.betas, 100)
+    assert list(steps) == list(range(0, 1000, 10)) and torch.equal(a, a2) and torch.equal(ap, ap2) and torch.equal(b, b2)
+    steps, a, ap, b = M._subsampled_schedule(net, 1000)
+    assert len(steps) == 1000 and torch.equal(b, net.betas)
