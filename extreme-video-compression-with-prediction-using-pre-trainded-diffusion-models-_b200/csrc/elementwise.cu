@@ -20,7 +20,15 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   u.w = pack_bf16x2(f[6], f[7]);
   return u;
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// streaming 16-byte load (read once: do not pollute L1)
+__device__ __forceinline__ uint4 ld_nc16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
 
 // ---------------------------------------------------------------------------------------------
 // GroupNorm statistics: per-(sample, channel) sum and sum of squares.  Deterministic two-level reduction:
@@ -29,7 +37,7 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x))
 // grid = (chunks, B), block = (nvec, rows) with nvec = C/8 channel vectors.
 // ---------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C,
-                                float* __restrict__ stats, int c_total, int c_off, int pix_per_block,
+                                long long* __restrict__ stats, int c_total, int c_off, int pix_per_block,
                                 float* __restrict__ partials, unsigned* __restrict__ tickets) {
   extern __shared__ float sred[];  // [rows][nvec][16]
   __shared__ unsigned s_last;
@@ -44,14 +52,32 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
   const __nv_bfloat16* xb = x + (long long)b * HW * ldx + v * 8;
-  for (int p = p_begin + r; p < p_end; p += blockDim.y) {
-    const uint4 u = *reinterpret_cast<const uint4*>(xb + (long long)p * ldx);
-    float f[8];
-    unpack8(u, f);
+  {
+    const int rows = blockDim.y;
+    int p = p_begin + r;
+    for (; p + 3 * rows < p_end; p += 4 * rows) {
+      uint4 u[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j] += f[j];
-      ss[j] = fmaf(f[j], f[j], ss[j]);
+      for (int k = 0; k < 4; ++k) u[k] = ld_nc16(xb + (long long)(p + k * rows) * ldx);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += f[j];
+          ss[j] = fmaf(f[j], f[j], ss[j]);
+        }
+      }
+    }
+    for (; p < p_end; p += rows) {
+      float f[8];
+      unpack8(ld_nc16(xb + (long long)p * ldx), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        ss[j] = fmaf(f[j], f[j], ss[j]);
+      }
     }
   }
   float* mine = sred + ((size_t)r * nvec + v) * 16;
@@ -90,68 +116,93 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
   for (int i = tid; i < 2 * C; i += nthr) {
     float acc = 0.f;
     for (int k = 0; k < chunks; ++k) acc += __ldcg(pb + (long long)k * C * 2 + i);
-    stats[((long long)b * c_total + c_off) * 2 + i] = acc;
+    stats[((long long)b * c_total + c_off) * 2 + i] = __float2ll_rn(acc * 1048576.f);
   }
   if (tid == 0) tickets[b] = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Normalise + (AdaGN | affine) + SiLU over the virtual concat [x0 | x1]; writes one contiguous tensor.
-// grid = (chunks, B), block = 256.  Per-channel a[c], b[c] (y = x*a + b) are built once per block in smem.
+// grid = (chunks, B), block = (nvec, rows): a thread owns 8 fixed channels (its y = x*a + b coefficients live in
+// registers) and streams pixels with 4 independent 16-byte loads in flight.  Group statistics are rebuilt per
+// block from the per-channel sums: one warp per group, shuffle tree (deterministic).
 // ---------------------------------------------------------------------------------------------
-__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1,
-                                int C1, int HW, const float* __restrict__ stats0, const float* __restrict__ stats1,
-                                int groups, float eps,
-                                const float* __restrict__ ss, int adagn, int silu, __nv_bfloat16* __restrict__ y,
-                                int pix_per_block) {
-  extern __shared__ float sab[];  // a[C] | b[C]
+__global__ void __launch_bounds__(1024) gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
+                                                       const __nv_bfloat16* __restrict__ x1, int C1, int HW,
+                                                       const long long* __restrict__ stats0,
+                                                       const long long* __restrict__ stats1, int groups, float eps,
+                                                       const float* __restrict__ ss, int adagn, int silu,
+                                                       __nv_bfloat16* __restrict__ y, int pix_per_block) {
+  __shared__ float s_mean[64], s_rstd[64];
   const int C = C0 + C1;
-  float* sa = sab;
-  float* sb = sab + C;
   const int b = blockIdx.y;
   const int cpg = C / groups;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
   const float inv_n = 1.f / ((float)cpg * (float)HW);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
+  for (int g = warp; g < groups; g += nwarps) {
     float s = 0.f, q = 0.f;
-    for (int j = 0; j < cpg; ++j) {
+    for (int j = lane; j < cpg; j += 32) {
       const int cc = g * cpg + j;
-      const float* st = (cc < C0) ? stats0 + ((long long)b * C0 + cc) * 2 : stats1 + ((long long)b * C1 + (cc - C0)) * 2;
-      s += st[0];
-      q += st[1];
+      const long long* st = (cc < C0) ? stats0 + ((long long)b * C0 + cc) * 2 : stats1 + ((long long)b * C1 + (cc - C0)) * 2;
+      s += (float)((double)st[0] * (1.0 / 1048576.0));
+      q += (float)((double)st[1] * (1.0 / 1048576.0));
     }
-    const float mean = s * inv_n;
-    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    const float gam = adagn ? (1.f + ss[c]) : ss[c];
-    const float bet = ss[C + c];
-    sa[c] = rstd * gam;
-    sb[c] = bet - mean * rstd * gam;
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) {
+      const float mean = s * inv_n;
+      const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+      s_mean[g] = mean;
+      s_rstd[g] = rsqrtf(var + eps);
+    }
   }
   __syncthreads();
-  const int nvec = C / 8;
-  const int nvec0 = C0 / 8;
+  const int v = threadIdx.x;  // channel vector
+  const int c = v * 8;
+  float a[8], bb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    const float gam = adagn ? (1.f + ss[c + j]) : ss[c + j];
+    a[j] = s_rstd[g] * gam;
+    bb[j] = ss[C + c + j] - s_mean[g] * a[j];
+  }
+  const bool first = (c < C0);
+  const __nv_bfloat16* src = first ? x0 + c : x1 + (c - C0);
+  const int ld = first ? C0 : C1;
+  src += (long long)b * HW * ld;
+  __nv_bfloat16* dst = y + (long long)b * HW * C + c;
+  const int rows = blockDim.y;
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(HW, p_begin + pix_per_block);
-  const long long total = (long long)(p_end - p_begin) * nvec;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-    const int p = p_begin + (int)(i / nvec);
-    const int v = (int)(i % nvec);
-    const long long row = (long long)b * HW + p;
-    uint4 u;
-    if (v < nvec0)
-      u = *reinterpret_cast<const uint4*>(x0 + row * C0 + v * 8);
-    else
-      u = *reinterpret_cast<const uint4*>(x1 + row * C1 + (v - nvec0) * 8);
+  int p = p_begin + threadIdx.y;
+  for (; p + 3 * rows < p_end; p += 4 * rows) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = ld_nc16(src + (long long)(p + k * rows) * ld);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8(u[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(f[j], a[j], bb[j]);
+        f[j] = silu ? silu_f(t) : t;
+      }
+      *reinterpret_cast<uint4*>(dst + (long long)(p + k * rows) * C) = pack8(f);
+    }
+  }
+  for (; p < p_end; p += rows) {
     float f[8];
-    unpack8(u, f);
-    const int c = v * 8;
+    unpack8(ld_nc16(src + (long long)p * ld), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float t = fmaf(f[j], sa[c + j], sb[c + j]);
+      const float t = fmaf(f[j], a[j], bb[j]);
       f[j] = silu ? silu_f(t) : t;
     }
-    *reinterpret_cast<uint4*>(y + row * C + c) = pack8(f);
+    *reinterpret_cast<uint4*>(dst + (long long)p * C) = pack8(f);
   }
 }
 
@@ -334,7 +385,7 @@ extern "C" int evc_gn_stats_workspace(int32_t B, int32_t HW, int32_t C, int64_t*
   return EVC_OK;
 }
 
-extern "C" int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, float* stats,
+extern "C" int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, int64_t* stats,
                             int32_t c_total, int32_t c_off, void* workspace, int64_t workspace_bytes,
                             evc_stream_t stream) {
   if (!x || !stats || !workspace || B < 1 || HW < 1 || C < 8 || (C % 8) || (ldx % 8) || (c_off % 8))
@@ -362,29 +413,38 @@ extern "C" int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, i
   dim3 block(nvec, rows), grid(chunks, B);
   const size_t smem = (size_t)rows * nvec * 16 * sizeof(float);
   gn_stats_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C,
-                                                               stats, c_total, c_off, ppb, partials, tickets);
+                                                               reinterpret_cast<long long*>(stats), c_total, c_off, ppb, partials, tickets);
   return evc_check_launch("gn_stats_kernel");
 }
 
 extern "C" int evc_gn_apply(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int32_t HW,
-                            const float* stats0, const float* stats1, int32_t groups, float eps, const float* ss,
+                            const int64_t* stats0, const int64_t* stats1, int32_t groups, float eps, const float* ss,
                             int32_t adagn, int32_t silu, void* y, evc_stream_t stream) {
   if (!x0 || !stats0 || (x1 != nullptr && stats1 == nullptr) || !ss || !y || B < 1 || HW < 1 || C0 < 8 || (C0 % 8) || (C1 % 8) || (x1 == nullptr && C1 != 0) ||
       groups < 1 || ((C0 + C1) % groups))
     return evc_set_error(EVC_ERR_INVALID, "evc_gn_apply: bad arguments");
   const int C = C0 + C1;
+  const int nvec = C / 8;
+  if (nvec > 256 || groups > 64) return evc_set_error(EVC_ERR_INVALID, "evc_gn_apply: C > 2048 or groups > 64");
+  // (block = nvec x rows threads <= 1024: rows <= 4 whenever nvec > 32 because nvec*rows is rounded to whole warps)
+  // whole warps only (the group statistics use warp shuffles): rows is a multiple of 32 / gcd(nvec, 32)
+  int g32 = 32, t = nvec;
+  while (t) { const int r2 = g32 % t; g32 = t; t = r2; }
+  const int step = 32 / g32;
+  int rows = (256 / nvec) / step * step;
+  if (rows < step) rows = step;
+  if (nvec * rows > 1024) return evc_set_error(EVC_ERR_INVALID, "evc_gn_apply: unsupported channel count");
   const int sms = evc_num_sms();
-  int chunks = (sms * 8 + B - 1) / B;
-  if (chunks > HW) chunks = HW;
+  int chunks = (sms * 6 + B - 1) / B;
+  const int max_chunks = (HW + rows - 1) / rows;
+  if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   const int ppb = (HW + chunks - 1) / chunks;
   chunks = (HW + ppb - 1) / ppb;
-  dim3 grid(chunks, B);
-  const size_t smem = (size_t)2 * C * sizeof(float);
-  if (smem > 48 * 1024) return evc_set_error(EVC_ERR_INVALID, "evc_gn_apply: C too large");
-  gn_apply_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1, HW, stats0, stats1,
-      groups, eps, ss, adagn, silu, reinterpret_cast<__nv_bfloat16*>(y), ppb);
+  dim3 grid(chunks, B), block(nvec, rows);
+  gn_apply_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1, HW, reinterpret_cast<const long long*>(stats0),
+      reinterpret_cast<const long long*>(stats1), groups, eps, ss, adagn, silu, reinterpret_cast<__nv_bfloat16*>(y), ppb);
   return evc_check_launch("gn_apply_kernel");
 }
 

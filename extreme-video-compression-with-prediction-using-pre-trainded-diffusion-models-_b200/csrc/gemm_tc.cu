@@ -44,6 +44,10 @@ struct alignas(64) GemmParams {
   long long resid_ld;
   float alpha;
   unsigned tx_bytes;
+  int resid_smem;  // 1: the epilogue stages residual rows in shared memory (cp.async prefetch)
+  long long* stats;  // optional fused GroupNorm statistics: (B, N, 2) fixed-point [sum, sumsq] of the stored bf16 values
+  int stats_combine;  // 1: the four epilogue warps of a tile belong to one sample (TW*TH == 128)
+  int sample_rows;    // TW*TH
 };
 
 __device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int& x0, int& y0, int& b0, int& n0) {
@@ -57,6 +61,25 @@ __device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int& 
   y0 = ty * p.TH;
   b0 = tb * p.TB;
   n0 = tn * p.BN;
+}
+
+// Column sums over the 32 rows held by a warp: v[j] is column j of this lane's row; afterwards v[0] of lane l is
+// the sum of column l over all 32 lanes.  31 shuffles (16+8+4+2+1) instead of 32 five-step reductions.
+__device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+constexpr float kStatScale = 1048576.f;  // 2^20 fixed point: integer atomics are order-independent => deterministic
+__device__ __forceinline__ void stat_add(long long* dst, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst), static_cast<unsigned long long>(__float2ll_rn(v * kStatScale)));
 }
 
 template <typename T>
@@ -210,11 +233,23 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
+    // Per tile: (1) while the main loop of this tile is still running, stage the bias slice in smem and
+    // prefetch this thread's residual row with cp.async (each thread only ever reads the row it copied, so no
+    // cross-thread synchronisation is needed for it); (2) wait for the accumulator; (3) TMEM -> registers ->
+    // +bias +residual, *alpha -> global.
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int e = threadIdx.x - 128;  // 0..127
     const int dx = row % p.TW;
     const int dy = (row / p.TW) % p.TH;
     const int db = row / (p.TW * p.TH);
+    uint8_t* gsm = smem_raw + (base - smem_u32(smem_raw));
+    float* sbias = reinterpret_cast<float*>(gsm + (bar_base - base) + 256);
+    const uint32_t res_pitch = static_cast<uint32_t>(p.BN) * 2u + 16u;
+    uint8_t* sres = gsm + (bar_base - base) + 256 + 1024 + static_cast<size_t>(row) * res_pitch;
+    const uint32_t sres_u32 = bar_base + 256u + 1024u + static_cast<uint32_t>(row) * res_pitch;
+    // [4 warps][BN][2] floats, after the residual rows
+    float* sstat = reinterpret_cast<float*>(gsm + (bar_base - base) + 256 + 1024 + (p.resid_smem ? 128u * res_pitch : 0u));
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -225,8 +260,24 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       const bool valid = (row < p.rows_valid) && (b < p.B);
       const long long pin = (long long)(y0 + dy) * p.W + (x0 + dx);
       const long long pix = (long long)b * p.H * p.W + pin;
+      const bool full_n = (n0 + p.BN <= p.N);
+      const bool resid_fast = (p.resid != nullptr) && p.resid_smem && full_n;
+      // (1) prefetch
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with the previous tile's sbias
+      if (p.bias != nullptr) {
+        for (int j = e; j < p.BN; j += 128) sbias[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      }
+      if (resid_fast && valid) {
+        const __nv_bfloat16* r = p.resid + pix * p.resid_ld + n0;
+        for (int j = 0; j < p.BN; j += 8)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sres_u32 + j * 2), "l"(r + j) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // sbias visible
+      // (2) accumulator ready
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         const int ncols = min(32, p.BN - c0);
@@ -236,46 +287,89 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         else
           tmem_ld_32x16(taddr + c0, v);
         tmem_ld_wait();
-        if (valid) {
-          const int n = n0 + c0;
-          float f[32];
+        if (c0 + 32 >= p.BN) {
+          // last TMEM read of this tile is complete: hand the accumulator stage back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+        const int n = n0 + c0;
+        float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = (j < ncols) ? __uint_as_float(v[j]) : 0.f;
+        for (int j = 0; j < 32; ++j) f[j] = (j < ncols) ? __uint_as_float(v[j]) : 0.f;
+        if (valid) {
           if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols && n + j < p.N) f[j] += __ldg(p.bias + n + j);
-          }
-          if (p.resid != nullptr) {
-            const __nv_bfloat16* r = p.resid + pix * p.resid_ld + n;
-            if (n + ncols <= p.N && (p.resid_ld & 7) == 0 && (p.N & 7) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (j < ncols) {
-                  const uint4 u = *reinterpret_cast<const uint4*>(r + j);
-                  f[j + 0] += bf16_lo(u.x);
-                  f[j + 1] += bf16_hi(u.x);
-                  f[j + 2] += bf16_lo(u.y);
-                  f[j + 3] += bf16_hi(u.y);
-                  f[j + 4] += bf16_lo(u.z);
-                  f[j + 5] += bf16_hi(u.z);
-                  f[j + 6] += bf16_lo(u.w);
-                  f[j + 7] += bf16_hi(u.w);
-                }
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) {
+                const float4 bv = *reinterpret_cast<const float4*>(sbias + c0 + j);
+                f[j + 0] += bv.x;
+                f[j + 1] += bv.y;
+                f[j + 2] += bv.z;
+                f[j + 3] += bv.w;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols && n + j < p.N) f[j] += __bfloat162float(r[j]);
             }
+          }
+          if (resid_fast) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < ncols) {
+                const uint4 u = *reinterpret_cast<const uint4*>(sres + (c0 + j) * 2);
+                f[j + 0] += bf16_lo(u.x);
+                f[j + 1] += bf16_hi(u.x);
+                f[j + 2] += bf16_lo(u.y);
+                f[j + 3] += bf16_hi(u.y);
+                f[j + 4] += bf16_lo(u.z);
+                f[j + 5] += bf16_hi(u.z);
+                f[j + 6] += bf16_lo(u.w);
+                f[j + 7] += bf16_hi(u.w);
+              }
+            }
+          } else if (p.resid != nullptr) {
+            const __nv_bfloat16* r = p.resid + pix * p.resid_ld + n;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols && n + j < p.N) f[j] += __bfloat162float(r[j]);
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
           store_chunk<float>(p, f, ncols, n, pix, b, pin);
         }
+        if (p.stats != nullptr) {
+          // statistics of the values as stored (bf16-rounded); rows outside the tensor contribute zero
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float r = (valid && j < ncols && n + j < p.N) ? __bfloat162float(__float2bfloat16_rn(f[j])) : 0.f;
+            f[j] = r;
+            sq[j] = r * r;
+          }
+          warp_transpose_sum(f, lane);
+          warp_transpose_sum(sq, lane);
+          if (p.stats_combine) {
+            sstat[(q * p.BN + c0 + lane) * 2 + 0] = f[0];
+            sstat[(q * p.BN + c0 + lane) * 2 + 1] = sq[0];
+          } else {
+            const int bw = b0 + (q * 32) / p.sample_rows;  // all 32 rows of this warp belong to one sample
+            if (bw < p.B && q * 32 < p.rows_valid && lane < ncols && n + lane < p.N) {
+              long long* dst = p.stats + ((long long)bw * p.N + n + lane) * 2;
+              stat_add(dst, f[0]);
+              stat_add(dst + 1, sq[0]);
+            }
+          }
+        }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      if (p.stats != nullptr && p.stats_combine) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (b0 < p.B) {
+          for (int i = e; i < 2 * p.BN; i += 128) {
+            const int col = i >> 1;
+            if (n0 + col < p.N) {
+              const float t = sstat[i] + sstat[2 * p.BN + i] + sstat[4 * p.BN + i] + sstat[6 * p.BN + i];
+              stat_add(p.stats + ((long long)b0 * p.N + n0 + col) * 2 + (i & 1), t);
+            }
+          }
+        }
+      }
     }
   }
 
@@ -421,11 +515,26 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   p.tx_bytes = (unsigned)(a_box_bytes + d->bn * 128);
 
   const int stage_bytes = kABytes + d->bn * 128;
-  int stages = (200 * 1024) / stage_bytes;
+  // shared memory: [stages][barriers 256 B][bias 1 KB][residual rows 128 x (2*BN + 16) B, only with a residual]
+  p.resid_smem = (d->resid != nullptr && (d->resid_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(d->resid) & 15) == 0 &&
+                  (d->w_rows % 8) == 0) ? 1 : 0;
+  p.stats = reinterpret_cast<long long*>(d->stats);
+  p.sample_rows = TW * TH;
+  p.stats_combine = (TW * TH == 128) ? 1 : 0;
+  if (d->stats != nullptr && (d->out_mode != EVC_OUT_BF16_ROWS || ((TW * TH) % 32) != 0)) {
+    delete pl;
+    return evc_set_error(EVC_ERR_INVALID, "fused GroupNorm statistics need bf16 row output and H*W % 32 == 0");
+  }
+  const int tail_bytes = 256 + 1024 + (p.resid_smem ? 128 * (d->bn * 2 + 16) : 0) + (d->stats ? 32 * d->bn : 0);
+  const int budget = 227 * 1024 - 1024 /*align slack*/ - tail_bytes;
+  int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) stages = 2;
+  if (stages < 2) {
+    delete pl;
+    return evc_set_error(EVC_ERR_INVALID, "tile does not fit in shared memory");
+  }
   p.num_stages = stages;
-  pl->smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  pl->smem_bytes = stages * stage_bytes + 1024 + tail_bytes;
 
   const long long tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
   int sms = evc_num_sms();

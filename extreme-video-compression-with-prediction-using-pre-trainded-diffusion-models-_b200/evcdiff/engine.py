@@ -78,6 +78,7 @@ class EngineBase:
         self.B, self.H = B, H
         self.pool = Pool(self.device)
         self.ops = []  # list of callables(label_idx)
+        self.op_info = []  # (kind, meta) per op, for profiling
         self.stats_slices = []  # (offset, numel) in the stats arena
         self.stats_total = 0
         self.flops = 0.0
@@ -88,8 +89,9 @@ class EngineBase:
         self.ws_bytes = 256
 
     # ----------------------------------------------------------------- recording helpers
-    def _op(self, fn):
+    def _op(self, fn, kind="other", meta=None):
         self.ops.append(fn)
+        self.op_info.append((kind, meta))
         self.n_launch += 1
 
     def new_act(self, H, W, C, scratch=True):
@@ -115,7 +117,7 @@ class EngineBase:
 
         def run(_):
             ops.gn_stats(act.t, act.B, act.H * act.W, act.C, act.stats, workspace=self.workspace)
-        self._op(run)
+        self._op(run, "gn_stats", dict(bytes=act.t.numel() * 2))
 
     def _stats_view(self, a):
         return a.stats
@@ -132,23 +134,28 @@ class EngineBase:
             ops.gn_apply(xa.t, xa.C, xb.t if xb is not None else None, xb.C if xb is not None else 0, xa.B,
                          xa.H * xa.W, self._stats_view(xa), self._stats_view(xb) if xb is not None else None,
                          groups, eps, ss_fn(li), adagn, silu, out.t)
-        self._op(run)
+        self._op(run, "gn_apply", dict(bytes=out.t.numel() * 4))
 
     def gemm(self, segs, w, out_t, out_mode, out_ld, out_bs=0, bias=None, resid=None, alpha=1.0, bias_fn=None):
         plan = ops.GemmPlan([(a.t if isinstance(a, Act) else a, taps) for a, taps in segs], w, out_t, out_mode,
                             out_ld, out_bs, bias=bias, resid=resid.t if isinstance(resid, Act) else resid,
                             resid_ld=(resid.C if isinstance(resid, Act) else 0), alpha=alpha)
         self.flops += plan.flops
+        a0 = segs[0][0]
+        shp = tuple(a0.t.shape) if isinstance(a0, Act) else tuple(a0.shape)
+        meta = dict(flops=plan.flops, M=shp[0] * shp[1] * shp[2], N=w.shape[-2], K=w.shape[-1],
+                    taps=[t for _, t in segs], hw=shp[2])
         if bias_fn is None:
-            self._op(lambda li: plan.launch())
+            self._op(lambda li: plan.launch(), "gemm", meta)
         else:
-            self._op(lambda li: plan.launch(bias_fn(li)))
+            self._op(lambda li: plan.launch(bias_fn(li)), "gemm", meta)
         return plan
 
     def fir(self, a, up):
         H2, W2 = (a.H * 2, a.W * 2) if up else (a.H // 2, a.W // 2)
         out = self.new_act(H2, W2, a.C)
-        self._op(lambda li: ops.fir_resample(a.t, out.t, a.B, a.H, a.W, a.C, up))
+        self._op(lambda li: ops.fir_resample(a.t, out.t, a.B, a.H, a.W, a.C, up), "fir",
+                 dict(bytes=(a.t.numel() + out.t.numel()) * 2))
         return out
 
     # ----------------------------------------------------------------- execution
@@ -164,6 +171,22 @@ class EngineBase:
         for fn in self.ops:
             fn(label_idx)
         return self.eps
+
+    def profile(self, label_idx=0, reps=3):
+        """Per-launch device time of one UNet evaluation (CUDA events around every launch, eager mode).
+        Returns [(kind, meta, best_ms)] in launch order; used by bench.py for the roofline of the GEMM kernel."""
+        n = len(self.ops)
+        best = [float("inf")] * n
+        for _ in range(reps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+            ev[0].record()
+            for i, fn in enumerate(self.ops):
+                fn(label_idx)
+                ev[i + 1].record()
+            torch.cuda.synchronize(self.device)
+            for i in range(n):
+                best[i] = min(best[i], ev[i].elapsed_time(ev[i + 1]))
+        return [(k, m, best[i]) for i, (k, m) in enumerate(self.op_info)]
 
 
 class NCSNppEngine(EngineBase):
@@ -359,7 +382,8 @@ class NCSNppEngine(EngineBase):
             q = qk3[:, :, hd * d:(hd + 1) * d].unsqueeze(1)  # (B,1,N,d)
             k = qk3[:, :, C + hd * d:C + (hd + 1) * d]  # (B,N,d)  per-sample B operand
             self.gemm([(q, 1)], k, S, EVC_OUT_F32_ROWS, Np, alpha=float(int(d) ** (-0.5)))
-            self._op(lambda li, S=S, Pm=Pm: ops.softmax_rows(S, Pm, B * N, Np))
+            self._op(lambda li, S=S, Pm=Pm: ops.softmax_rows(S, Pm, B * N, Np), "softmax",
+                     dict(bytes=B * N * Np * 6))
             self.gemm([(Pm.view(B, 1, N, Np), 1)], vT[:, hd * d:(hd + 1) * d, :], o3[:, :, hd * d:], EVC_OUT_BF16_ROWS, C)
         out = self.new_act(x.H, x.W, C, scratch=False)
         self.gemm([(o, 1)], wo.contiguous(), out.t, EVC_OUT_BF16_ROWS, C, bias=bo.contiguous(), resid=x, alpha=RSQRT2)

@@ -53,7 +53,8 @@ class GemmPlan:
         d.B, d.H, d.W = B, H, W_
         n = d.w_rows
         if bn is None:
-            bn = pick_bn(n)
+            kblocks = sum(taps * (-(-a.shape[3] // 64)) for a, taps in segs)
+            bn = pick_bn(n, m_tiles(B, H, W_, w.dim() == 3), kblocks)
         d.bn = bn
         d.out = out.data_ptr()
         d.out_mode = out_mode
@@ -85,12 +86,32 @@ class GemmPlan:
             pass
 
 
-def pick_bn(n):
-    """N tile for the 128-row UMMA: the widest of 256/192/128/64/... that divides N (else round N up to 16)."""
-    for bn in (256, 192, 128, 64, 32, 16):
-        if n % bn == 0:
-            return bn
-    return min(256, ((n + 15) // 16) * 16)
+def m_tiles(B, H, W, batched):
+    """Number of 128-pixel M tiles the kernel will use (mirrors evc_gemm_plan_create)."""
+    tw = min(W, 128)
+    th = max(1, min(H, 128 // tw))
+    tb = 1 if batched else max(1, 128 // (tw * th))
+    return (W // tw) * (H // th) * (-(-B // tb))
+
+
+def pick_bn(n, mt=None, kblocks=None, sms=148):
+    """N tile of the 128-row UMMA.  Large problems: the widest tile that divides N (fewest A re-reads, best
+    MMA efficiency).  Problems with few M tiles (8x8 / 16x16 levels, small batches): the tile that minimises
+    waves x per-tile time, so that all SMs get work."""
+    cands = [bn for bn in (256, 192, 128, 96, 64, 48, 32, 16) if n % bn == 0]
+    if not cands:
+        return min(256, ((n + 15) // 16) * 16)
+    if mt is None or kblocks is None:
+        return cands[0]
+    best, best_cost = None, None
+    for bn in cands:
+        tiles = mt * (n // bn)
+        waves = -(-tiles // sms)
+        # cycles: 4 MMAs of bn/2 cycles per 64-wide K block (min 32 each), + pipeline fill + epilogue
+        cost = waves * (kblocks * 4 * max(bn // 2, 32) + 1500 + 12 * bn)
+        if best_cost is None or cost < best_cost * 0.97:  # prefer wider tiles unless clearly slower
+            best, best_cost = bn, cost
+    return best
 
 
 def gn_stats_workspace_bytes(B, HW, Cc):

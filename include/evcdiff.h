@@ -88,6 +88,10 @@ typedef struct evc_gemm_desc {
   int64_t resid_ld;
   float alpha;
   int32_t max_ctas;   /* 0 = number of SMs */
+  /* optional fused GroupNorm statistics of the stored output (EVC_OUT_BF16_ROWS only, H*W % 32 == 0):
+   * stats[(b*N + n)*2 + {0,1}] += {sum, sum of squares} * 2^20 as 64-bit integers (order-independent, hence
+   * deterministic); the caller zeroes the buffer before the launch.  Same format as evc_gn_stats. */
+  int64_t* stats;
 } evc_gemm_desc;
 
 typedef struct evc_gemm_plan evc_gemm_plan;
@@ -104,22 +108,23 @@ double evc_gemm_plan_flops(const evc_gemm_plan* plan);
  * GroupNorm statistics and the fused normalise / AdaGN / affine / SiLU pass.
  * Replaces nn.GroupNorm + get_act_norm (layerspp.py:465-549) and Normalize+Swish (unet.py:44-46,90-95).
  * ---------------------------------------------------------------------------------------------- */
-/* stats[(b*c_total + c_off + c)*2 + {0,1}] = {sum, sum of squares} over the HW pixels of x (bf16 rows, row stride
- * ldx), C % 8 == 0.  Deterministic (no floating-point atomics).  `workspace` is caller-owned scratch of at least
+/* stats[(b*c_total + c_off + c)*2 + {0,1}] = {sum, sum of squares} * 2^20 (int64 fixed point) over the HW pixels of x
+ * (bf16 rows, row stride ldx), C % 8 == 0.  Deterministic (no floating-point atomics).  `workspace` is caller-owned scratch of at least
  * evc_gn_stats_workspace() bytes whose first bytes (the ticket counters) must be zero before the FIRST use; the
  * kernel leaves them zero, so one workspace can be shared by every call on the same stream. */
 int evc_gn_stats_workspace(int32_t B, int32_t HW, int32_t C, int64_t* bytes);
-int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, float* stats, int32_t c_total,
+int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, int64_t* stats, int32_t c_total,
                  int32_t c_off, void* workspace, int64_t workspace_bytes, evc_stream_t stream);
 
 /* y[b, p, c] = act( (x[b,p,c] - mean_g) * rstd_g * (gamma'[c]) + beta'[c] ), group g = c / (C/groups) over the
  * concatenation [x0 | x1] (x1 may be NULL).  mean/rstd come from the per-channel sums `stats0` (B,C0,2) and
- * `stats1` (B,C1,2) written by evc_gn_stats (biased variance, eps); a group may straddle the concat boundary.
+ * `stats1` (B,C1,2) (int64 fixed point, 2^20) written by evc_gn_stats or by the GEMM epilogue (biased variance,
+ * eps); a group may straddle the concat boundary.
  *   adagn != 0: gamma' = 1 + ss[c], beta' = ss[C + c]          (ss = Dense_0(SiLU(temb)) row, 2*C floats)
  *   adagn == 0: gamma' = ss[c], beta' = ss[C + c]              (GroupNorm affine weight | bias)
  * silu != 0 applies x*sigmoid(x).  Output bf16 rows with row stride C (materialises the concat). */
-int evc_gn_apply(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int32_t HW, const float* stats0,
-                 const float* stats1, int32_t groups, float eps, const float* ss, int32_t adagn, int32_t silu,
+int evc_gn_apply(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int32_t HW, const int64_t* stats0,
+                 const int64_t* stats1, int32_t groups, float eps, const float* ss, int32_t adagn, int32_t silu,
                  void* y, evc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -138,16 +138,27 @@ def test_samplers_vs_golden(small, tag, cfgf, seed, active):
     assert common.rel_l2(y, ref) < 2.5e-2, ("ddpm", common.rel_l2(y, ref))
     fr = lambda z: torch.clamp((z + 1) / 2, 0, 1)
     assert common.psnr(fr(y), fr(ref)) > 35.0
+    # DDIM / F-PNDM free-running trajectories are chaotic with untrained weights (a 1e-6 perturbation
+    # grows to O(1)), so they are checked by decomposition instead: (i) eps parity of the network (tests above),
+    # (ii) sampler arithmetic: our graph-captured sampler against the ORACLE sampler (pinned to the reference on
+    # CPU, tests/test_oracle.py) when both drive the same, bit-reproducible evcdiff network.
+    model = lambda xx, yy: net(xx, yy, cond=cond)
+    sched = (net.betas, net.alphas, net.alphas_prev)
     y = M.FPNDM_sampler(x_T.clone(), net, cond=cond, final_only=True, subsample_steps=10, clip_before=True)
-    ref = T(small[f"{tag}_fpndm10"])
-    # F-PNDM as the reference runs it (ascending indices) amplifies eps noise ~10x with untrained
-    # weights; the per-step arithmetic is checked exactly in test_elementwise_gpu.py
-    assert common.rel_l2(y, ref) < 8e-2, ("fpndm", common.rel_l2(y, ref))
+    seen = []
+    ref = S.fpndm_sampler(x_T.clone(), model, sched, subsample_steps=10, labels_seen=seen)
+    assert np.allclose(np.array(seen), small[f"{tag}_fpndm10_labels"])
+    assert common.rel_l2(y[0], ref) < 2e-3, ("fpndm", common.rel_l2(y[0], ref))
     y = M.ddim_sampler(x_T.clone(), net, cond=cond, final_only=True, denoise=True, subsample_steps=10,
                        clip_before=True)
-    ref = T(small[f"{tag}_ddim10"])
-    if not active:  # active-init DDIM is chaotic: checked teacher-forced below instead
-        assert common.rel_l2(y, ref) < XT_TOL, ("ddim", common.rel_l2(y, ref))
+    ref = S.ddim_sampler(x_T.clone(), model, sched, subsample_steps=10)
+    assert common.rel_l2(y[0], ref) < 2e-3, ("ddim", common.rel_l2(y[0], ref))
+    y = M.ddpm_sampler(x_T.clone(), net, cond=cond, final_only=True, denoise=True, subsample_steps=10,
+                       clip_before=True, noise=tape)
+    ref = S.ddpm_sampler(x_T.clone(), model, sched, lambda i: tape[i].to(DEV), subsample_steps=10)
+    assert common.rel_l2(y[0], ref) < 2e-3, ("ddpm", common.rel_l2(y[0], ref))
+    imgs = M.FPNDM_sampler(x_T.clone(), net, cond=cond, final_only=False, subsample_steps=10)
+    assert imgs.shape == (10,) + tuple(x_T.shape) and imgs.device.type == "cpu"
 
 
 def test_teacher_forced_steps_and_graph_equals_eager():
