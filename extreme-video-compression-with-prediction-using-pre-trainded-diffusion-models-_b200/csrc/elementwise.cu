@@ -352,7 +352,11 @@ __global__ void pack_nchw_kernel(const T* __restrict__ src, int B, int C, int HW
     const int p = (int)(i % HW);
     const T* s = src + (long long)b * C * HW + p;
     __nv_bfloat16* d = dst + i * Cpad + c_off;
-    for (int c = 0; c < C; ++c) d[c] = __float2bfloat16_rn(fmaf((float)s[(long long)c * HW], scale, shift));
+    // evaluated in the source precision with separate multiply / add, like the reference's `2 * X - 1.`
+    for (int c = 0; c < C; ++c) {
+      const T v = s[(long long)c * HW] * (T)scale;
+      d[c] = __float2bfloat16_rn((float)(v + (T)shift));
+    }
   }
 }
 

@@ -346,8 +346,10 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           warp_transpose_sum(f, lane);
           warp_transpose_sum(sq, lane);
           if (p.stats_combine) {
-            sstat[(q * p.BN + c0 + lane) * 2 + 0] = f[0];
-            sstat[(q * p.BN + c0 + lane) * 2 + 1] = sq[0];
+            if (lane < ncols) {
+              sstat[(q * p.BN + c0 + lane) * 2 + 0] = f[0];
+              sstat[(q * p.BN + c0 + lane) * 2 + 1] = sq[0];
+            }
           } else {
             const int bw = b0 + (q * 32) / p.sample_rows;  // all 32 rows of this warp belong to one sample
             if (bw < p.B && q * 32 < p.rows_valid && lane < ncols && n + lane < p.N) {

@@ -86,6 +86,7 @@ class EngineBase:
         self.taps = {}
         self._keep = []
         self._stat_acts = []
+        self._deferred = []
         self.ws_bytes = 256
 
     # ----------------------------------------------------------------- recording helpers
@@ -104,13 +105,22 @@ class EngineBase:
             if a is not None:
                 self.pool.put(a.t)
 
-    def ensure_stats(self, a):
-        if a.stats is not None:
-            return
+    def alloc_stats(self, a):
         n = a.B * a.C * 2
         a.stats = ("slice", self.stats_total, n)
         self.stats_total += n
         self._stat_acts.append(a)
+
+    @staticmethod
+    def can_fuse_stats(H, W):
+        tw = min(W, 128)
+        th = max(1, min(H, 128 // tw))
+        return (tw * th) % 32 == 0
+
+    def ensure_stats(self, a):
+        if a.stats is not None:
+            return
+        self.alloc_stats(a)
         act = a
 
         self.ws_bytes = max(self.ws_bytes, ops.gn_stats_workspace_bytes(act.B, act.H * act.W, act.C))
@@ -136,10 +146,31 @@ class EngineBase:
                          groups, eps, ss_fn(li), adagn, silu, out.t)
         self._op(run, "gn_apply", dict(bytes=out.t.numel() * 4))
 
-    def gemm(self, segs, w, out_t, out_mode, out_ld, out_bs=0, bias=None, resid=None, alpha=1.0, bias_fn=None):
+    def gemm(self, segs, w, out_t, out_mode, out_ld, out_bs=0, bias=None, resid=None, alpha=1.0, bias_fn=None,
+             stats_of=None):
+        """stats_of: the Act being written; when given (and the tile geometry allows it) its GroupNorm statistics
+        are accumulated by the GEMM epilogue and no separate gn_stats launch is recorded for it."""
+        stats_t = None
+        if stats_of is not None and out_mode == EVC_OUT_BF16_ROWS and self.can_fuse_stats(stats_of.H, stats_of.W):
+            self.alloc_stats(stats_of)
+            stats_t = ("deferred", stats_of)
+        plan_args = dict(out_bs=out_bs, bias=bias, resid=resid.t if isinstance(resid, Act) else resid,
+                         resid_ld=(resid.C if isinstance(resid, Act) else 0), alpha=alpha)
+        if stats_t is not None:
+            # the arena does not exist yet: create the plan in finalize()
+            self._deferred.append((len(self.ops), [(a.t if isinstance(a, Act) else a, taps) for a, taps in segs], w,
+                                   out_t, out_mode, out_ld, plan_args, stats_of))
+            plan = None
+            flops = 2.0 * out_t.shape[0] * stats_of.H * stats_of.W * w.shape[-2] * w.shape[-1]
+            self.flops += flops
+            a0 = segs[0][0]
+            shp = tuple(a0.t.shape) if isinstance(a0, Act) else tuple(a0.shape)
+            meta = dict(flops=flops, M=shp[0] * shp[1] * shp[2], N=w.shape[-2], K=w.shape[-1],
+                        taps=[t for _, t in segs], hw=shp[2])
+            self._op(None, "gemm", meta)
+            return None
         plan = ops.GemmPlan([(a.t if isinstance(a, Act) else a, taps) for a, taps in segs], w, out_t, out_mode,
-                            out_ld, out_bs, bias=bias, resid=resid.t if isinstance(resid, Act) else resid,
-                            resid_ld=(resid.C if isinstance(resid, Act) else 0), alpha=alpha)
+                            out_ld, **plan_args)
         self.flops += plan.flops
         a0 = segs[0][0]
         shp = tuple(a0.t.shape) if isinstance(a0, Act) else tuple(a0.shape)
@@ -160,14 +191,19 @@ class EngineBase:
 
     # ----------------------------------------------------------------- execution
     def finalize(self):
-        self.stats_arena = torch.zeros(max(self.stats_total, 2), dtype=torch.float32, device=self.device)
+        self.stats_arena = torch.zeros(max(self.stats_total, 2), dtype=torch.int64, device=self.device)
         self.workspace = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.device)
         for a in self._stat_acts:
             _, off, n = a.stats
             a.stats = self.stats_arena[off:off + n]
+        for idx, segs, w, out_t, out_mode, out_ld, plan_args, act in self._deferred:
+            plan = ops.GemmPlan(segs, w, out_t, out_mode, out_ld, stats=act.stats, **plan_args)
+            self.ops[idx] = (lambda li, plan=plan: plan.launch())
+        self._deferred = []
 
     def forward(self, label_idx=0):
         """Enqueue one UNet evaluation: reads self.xin, writes self.eps (B, C_out, H, W) fp32."""
+        ops.fill_zero(self.stats_arena)  # fused statistics accumulate with integer atomics
         for fn in self.ops:
             fn(label_idx)
         return self.eps
@@ -258,7 +294,7 @@ class NCSNppEngine(EngineBase):
         i = 2
         h0 = self.new_act(H, H, spec[i]["cout"], scratch=False)
         self.gemm([(xin, 9)], pack_conv3(sd[P(i) + ".weight"].to(dev), CIN_PAD), h0.t, EVC_OUT_BF16_ROWS, h0.C,
-                  bias=self.f32(P(i) + ".bias"))
+                  bias=self.f32(P(i) + ".bias"), stats_of=h0)
         self.taps["m2"] = h0
         i += 1
         hs = [h0]
@@ -322,7 +358,7 @@ class NCSNppEngine(EngineBase):
             tmp += xs
         c0 = self.new_act(h.H, h.W, cout)
         self.gemm([(h, 9)], pack_conv3(sd[P(i) + ".Conv_0.weight"].to(dev)), c0.t, EVC_OUT_BF16_ROWS, cout,
-                  bias=self.f32(P(i) + ".Conv_0.bias"))
+                  bias=self.f32(P(i) + ".Conv_0.bias"), stats_of=c0)
         self.release(h)
         a1 = self.new_act(c0.H, c0.W, cout)
         self.gn_apply(c0, None, self._ss(i, 1), 1e-5, True, True, a1)
@@ -334,12 +370,14 @@ class NCSNppEngine(EngineBase):
             w = torch.cat([w1, w2], dim=1).contiguous()
             bias = (b1 + sd[P(i) + ".Conv_2.bias"].float()).to(dev).contiguous()
             self._keep.append(bias)
-            self.gemm([(a1, 9)] + [(x, 1) for x in xs], w, out.t, EVC_OUT_BF16_ROWS, cout, bias=bias, alpha=RSQRT2)
+            self.gemm([(a1, 9)] + [(x, 1) for x in xs], w, out.t, EVC_OUT_BF16_ROWS, cout, bias=bias, alpha=RSQRT2,
+                      stats_of=out)
         else:
             assert len(xs) == 1 and xs[0].C == cout
             bias = b1.to(dev).contiguous()
             self._keep.append(bias)
-            self.gemm([(a1, 9)], w1, out.t, EVC_OUT_BF16_ROWS, cout, bias=bias, resid=xs[0], alpha=RSQRT2)
+            self.gemm([(a1, 9)], w1, out.t, EVC_OUT_BF16_ROWS, cout, bias=bias, resid=xs[0], alpha=RSQRT2,
+                      stats_of=out)
         self.release(c0, a1, *tmp)
         self.taps[f"m{i}"] = out
         return out
@@ -386,7 +424,8 @@ class NCSNppEngine(EngineBase):
                      dict(bytes=B * N * Np * 6))
             self.gemm([(Pm.view(B, 1, N, Np), 1)], vT[:, hd * d:(hd + 1) * d, :], o3[:, :, hd * d:], EVC_OUT_BF16_ROWS, C)
         out = self.new_act(x.H, x.W, C, scratch=False)
-        self.gemm([(o, 1)], wo.contiguous(), out.t, EVC_OUT_BF16_ROWS, C, bias=bo.contiguous(), resid=x, alpha=RSQRT2)
+        self.gemm([(o, 1)], wo.contiguous(), out.t, EVC_OUT_BF16_ROWS, C, bias=bo.contiguous(), resid=x, alpha=RSQRT2,
+                  stats_of=out)
         self.pool.put(qk)
         if Np == N:
             self.pool.put(vT); self.pool.put(S); self.pool.put(Pm)

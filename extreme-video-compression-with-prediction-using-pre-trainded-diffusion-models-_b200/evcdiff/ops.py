@@ -27,7 +27,7 @@ class GemmPlan:
     """
 
     def __init__(self, segs, w, out, out_mode, out_ld, out_bs=0, bias=None, resid=None, resid_ld=0, alpha=1.0,
-                 bn=None, max_ctas=0):
+                 bn=None, max_ctas=0, stats=None):
         lib = load()
         _require_cuda(w, out, bias, resid, *[s[0] for s in segs])
         d = GemmDesc()
@@ -67,7 +67,10 @@ class GemmPlan:
         d.resid_ld = resid_ld
         d.alpha = alpha
         d.max_ctas = max_ctas
-        self._keep = (segs, w, out, bias, resid)
+        if stats is not None:
+            assert stats.dtype == torch.int64 and stats.is_cuda
+            d.stats = stats.data_ptr()
+        self._keep = (segs, w, out, bias, resid, stats)
         self._lib = lib
         h = C.c_void_p()
         check(lib.evc_gemm_plan_create(C.byref(d), C.byref(h)), "evc_gemm_plan_create")
@@ -133,7 +136,7 @@ def _default_workspace(device, nbytes):
 
 
 def gn_stats(x, B, HW, C, stats, ldx=None, workspace=None):
-    """stats (B,C,2) fp32 = per-channel [sum, sumsq] of x (B*HW rows of C bf16).  workspace: zero-initialised
+    """stats (B,C,2) int64 (2^20 fixed point) = per-channel [sum, sumsq] of x (B*HW rows of C bf16).  workspace: zero-initialised
     uint8 scratch (shared between calls on one stream); a per-device default is used when omitted."""
     _require_cuda(x, stats)
     if workspace is None:

@@ -123,3 +123,30 @@ def test_strided_views_and_repeat_launch():
     torch.cuda.synchronize()
     ref = torch.bmm(q[:, 0].float(), k.float().transpose(1, 2)) * 192 ** -0.5
     assert rel_l2(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("B,H,Cin,N,resid", [(2, 128, 64, 192, False), (3, 32, 192, 384, True), (5, 8, 192, 768, True),
+                                              (2, 16, 128, 576, False), (1, 8, 192, 768, True), (1, 16, 64, 48, False)])
+def test_fused_groupnorm_statistics(B, H, Cin, N, resid):
+    """Epilogue-fused per-(sample, channel) [sum, sumsq] (int64, 2^20 fixed point) of the stored bf16 output."""
+    ops = _setup()
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H)
+    a = torch.randn(B, H, H, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, 9 * Cin, device="cuda", generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    r = torch.randn(B, H, H, N, device="cuda", generator=g).bfloat16() if resid else None
+    out = torch.zeros(B, H, H, N, device="cuda", dtype=torch.bfloat16)
+    stats = torch.zeros(B, N, 2, device="cuda", dtype=torch.int64)
+    plan = ops.GemmPlan([(a, 9)], w, out, 0, out_ld=N, bias=bias, resid=r, resid_ld=N, alpha=0.7071, stats=stats)
+    plan.launch()
+    torch.cuda.synchronize()
+    ref = ref_conv([(a, 9)], w, bias, r, 0.7071)
+    assert rel_l2(out.float().permute(0, 3, 1, 2), ref) < 4e-3
+    o = out.double()
+    assert rel_l2(stats[..., 0].double() / 2 ** 20, o.sum((1, 2))) < 1e-5
+    assert rel_l2(stats[..., 1].double() / 2 ** 20, (o * o).sum((1, 2))) < 1e-5
+    s1 = stats.clone()
+    stats.zero_()
+    plan.launch()
+    torch.cuda.synchronize()
+    assert torch.equal(s1, stats)  # integer atomics: bit-reproducible
