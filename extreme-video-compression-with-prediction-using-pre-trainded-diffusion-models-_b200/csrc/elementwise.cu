@@ -212,44 +212,63 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const __nv_bfloat16* __r
 //   down: out[i]    = (x[2i-1] + 3 x[2i] + 3 x[2i+1] + x[2i+2]) / 8                  (per axis)
 // One thread = one output pixel x 8 channels.
 // ---------------------------------------------------------------------------------------------
+// One thread = one INPUT pixel x 8 channels -> the 2x2 output pixels it expands to (3x3 input neighbourhood,
+// 9 loads for 4 stores instead of 16).  Horizontal pass first: L = (x[i-1] + 3 x[i]) / 4, R = (3 x[i] + x[i+1]) / 4.
 __global__ void fir_up_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W,
                               int C) {
   const int nvec = C / 8;
-  const int OH = 2 * H, OW = 2 * W;
-  const long long total = (long long)B * OH * OW * nvec;
+  const int OW = 2 * W;
+  const long long total = (long long)B * H * W * nvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % nvec);
     long long t = i / nvec;
-    const int ox = (int)(t % OW);
-    t /= OW;
-    const int oy = (int)(t % OH);
-    const int b = (int)(t / OH);
-    // axis taps: even -> (i-1: 1/4, i: 3/4); odd -> (i: 3/4, i+1: 1/4)
-    const int iy = oy >> 1, ix = ox >> 1;
-    const int y2 = (oy & 1) ? iy + 1 : iy - 1;
-    const int x2 = (ox & 1) ? ix + 1 : ix - 1;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int ix = (int)(t % W);
+    t /= W;
+    const int iy = (int)(t % H);
+    const int b = (int)(t / H);
     const __nv_bfloat16* xb = x + (long long)b * H * W * C + v * 8;
+    float hl[3][8], hr[3][8];
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int yy = a ? y2 : iy;
-      const float wy = a ? 0.25f : 0.75f;
-      if (yy < 0 || yy >= H) continue;
+    for (int r = 0; r < 3; ++r) {
+      const int yy = iy - 1 + r;
+      if (yy < 0 || yy >= H) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int xx = c ? x2 : ix;
-        const float w = wy * (c ? 0.25f : 0.75f);
-        if (xx < 0 || xx >= W) continue;
-        const uint4 u = *reinterpret_cast<const uint4*>(xb + ((long long)yy * W + xx) * C);
-        float f[8];
-        unpack8(u, f);
+        for (int j = 0; j < 8; ++j) hl[r][j] = hr[r][j] = 0.f;
+        continue;
+      }
+      const __nv_bfloat16* row = xb + (long long)yy * W * C;
+      float c0[8], cm[8], cp[8];
+      unpack8(ld_nc16(row + (long long)ix * C), c0);
+      if (ix > 0) unpack8(ld_nc16(row + (long long)(ix - 1) * C), cm);
+      else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, f[j], acc[j]);
+        for (int j = 0; j < 8; ++j) cm[j] = 0.f;
+      }
+      if (ix + 1 < W) unpack8(ld_nc16(row + (long long)(ix + 1) * C), cp);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cp[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        hl[r][j] = 0.25f * cm[j] + 0.75f * c0[j];
+        hr[r][j] = 0.75f * c0[j] + 0.25f * cp[j];
       }
     }
-    *reinterpret_cast<uint4*>(y + (((long long)b * OH + oy) * OW + ox) * C + v * 8) = pack8(acc);
+    float o[8];
+    __nv_bfloat16* yb = y + (((long long)b * 2 * H + 2 * iy) * OW + 2 * ix) * C + v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.25f * hl[0][j] + 0.75f * hl[1][j];
+    *reinterpret_cast<uint4*>(yb) = pack8(o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.25f * hr[0][j] + 0.75f * hr[1][j];
+    *reinterpret_cast<uint4*>(yb + C) = pack8(o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.75f * hl[1][j] + 0.25f * hl[2][j];
+    *reinterpret_cast<uint4*>(yb + (long long)OW * C) = pack8(o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.75f * hr[1][j] + 0.25f * hr[2][j];
+    *reinterpret_cast<uint4*>(yb + (long long)OW * C + C) = pack8(o);
   }
 }
 
@@ -279,7 +298,7 @@ __global__ void fir_down_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
         const int xx = 2 * ox - 1 + c;
         if (xx < 0 || xx >= W) continue;
         const float w = k[a] * k[c];
-        const uint4 u = *reinterpret_cast<const uint4*>(xb + ((long long)yy * W + xx) * C);
+        const uint4 u = ld_nc16(xb + ((long long)yy * W + xx) * C);
         float f[8];
         unpack8(u, f);
 #pragma unroll
@@ -456,8 +475,8 @@ extern "C" int evc_fir_resample(const void* x, void* y, int32_t B, int32_t H, in
                                 evc_stream_t stream) {
   if (!x || !y || B < 1 || H < 1 || W < 1 || C < 8 || (C % 8) || (!up && ((H | W) & 1)))
     return evc_set_error(EVC_ERR_INVALID, "evc_fir_resample: bad arguments");
-  const long long outpix = up ? (long long)B * 4 * H * W : (long long)B * (H / 2) * (W / 2);
-  const long long items = outpix * (C / 8);
+  const long long work = up ? (long long)B * H * W : (long long)B * (H / 2) * (W / 2);  // threads: input px (up) / output px
+  const long long items = work * (C / 8);
   const int grid = grid_for(items, 256);
   if (up)
     fir_up_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),

@@ -17,7 +17,8 @@ namespace evc {
 
 constexpr int kMaxStages = 8;
 constexpr int kABytes = 128 * 64 * 2;  // one A stage: 128 rows x 64 bf16
-constexpr int kThreads = 256;
+constexpr int kEpiThreads = 256;  // 8 epilogue warps: two per TMEM lane quarter, alternating 32-column chunks
+constexpr int kThreads = 128 + kEpiThreads;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 
@@ -48,6 +49,7 @@ struct alignas(64) GemmParams {
   long long* stats;  // optional fused GroupNorm statistics: (B, N, 2) fixed-point [sum, sumsq] of the stored bf16 values
   int stats_combine;  // 1: the four epilogue warps of a tile belong to one sample (TW*TH == 128)
   int sample_rows;    // TW*TH
+  int stride;         // convolution stride (1 or 2): input coordinate = stride * output coordinate + tap offset
 };
 
 __device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int& x0, int& y0, int& b0, int& n0) {
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), kEpiThreads);
     }
     fence_mbar_init();
   }
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), p.tx_bytes);
             const uint32_t sa = base + stage * stage_bytes;
-            tma_load_4d(&p.a_map[s], sa, full_bar(stage), c * 64, x0 + dx, y0 + dy, b0);
+            tma_load_4d(&p.a_map[s], sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
             tma_load_3d(&p.b_map, sa + kABytes, full_bar(stage), ktap + c * 64, n0, zb);
             if (++stage == p.num_stages) {
               stage = 0;
@@ -237,9 +239,10 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     // prefetch this thread's residual row with cp.async (each thread only ever reads the row it copied, so no
     // cross-thread synchronisation is needed for it); (2) wait for the accumulator; (3) TMEM -> registers ->
     // +bias +residual, *alpha -> global.
-    const int q = warp & 3;
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int grp = (warp - 4) >> 2;   // 0/1: which 32-column chunks (even/odd) this warp handles
     const int row = q * 32 + lane;
-    const int e = threadIdx.x - 128;  // 0..127
+    const int e = threadIdx.x - 128;  // 0..kEpiThreads-1
     const int dx = row % p.TW;
     const int dy = (row / p.TW) % p.TH;
     const int db = row / (p.TW * p.TH);
@@ -263,23 +266,27 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       const bool full_n = (n0 + p.BN <= p.N);
       const bool resid_fast = (p.resid != nullptr) && p.resid_smem && full_n;
       // (1) prefetch
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with the previous tile's sbias
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone is done with the previous tile's sbias
       if (p.bias != nullptr) {
-        for (int j = e; j < p.BN; j += 128) sbias[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+        for (int j = e; j < p.BN; j += kEpiThreads) sbias[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
       }
       if (resid_fast && valid) {
         const __nv_bfloat16* r = p.resid + pix * p.resid_ld + n0;
-        for (int j = 0; j < p.BN; j += 8)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sres_u32 + j * 2), "l"(r + j) : "memory");
+        for (int c0 = grp * 32; c0 < p.BN; c0 += 64)  // only the chunks this thread will consume
+#pragma unroll
+          for (int j = c0; j < c0 + 32; j += 8)
+            if (j < p.BN)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sres_u32 + j * 2), "l"(r + j) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // sbias visible
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // sbias visible
       // (2) accumulator ready
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      bool released = false;
+      for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
         const int ncols = min(32, p.BN - c0);
         uint32_t v[32];
         if (ncols == 32)
@@ -287,7 +294,8 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         else
           tmem_ld_32x16(taddr + c0, v);
         tmem_ld_wait();
-        if (c0 + 32 >= p.BN) {
+        if (c0 + 64 >= p.BN) {
+          released = true;
           // last TMEM read of this tile is complete: hand the accumulator stage back to the MMA warp
           tc_fence_before();
           mbar_arrive(tempty_bar(acc));
@@ -360,10 +368,14 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           }
         }
       }
+      if (!released) {  // this warp had no chunk in this tile (BN <= 32 and grp == 1)
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));
+      }
       if (p.stats != nullptr && p.stats_combine) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (b0 < p.B) {
-          for (int i = e; i < 2 * p.BN; i += 128) {
+          for (int i = e; i < 2 * p.BN; i += kEpiThreads) {
             const int col = i >> 1;
             if (n0 + col < p.N) {
               const float t = sstat[i] + sstat[2 * p.BN + i] + sstat[4 * p.BN + i] + sstat[6 * p.BN + i];
@@ -396,10 +408,11 @@ struct evc_gemm_plan {
 };
 
 static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box) {
+                      const uint32_t* box, int conv_stride = 1) {
   PFN_encodeTiled enc = evc_get_encode_tiled();
   if (enc == nullptr) return evc_set_error(EVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   uint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (rank == 4) estr[1] = estr[2] = (uint32_t)conv_stride;  // W and H traversal stride of a strided convolution
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -454,6 +467,12 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   p.N = d->w_rows;
   p.tiles_n = (d->w_rows + d->bn - 1) / d->bn;
 
+  const int cs = d->stride <= 1 ? 1 : d->stride;
+  if (cs != 1 && cs != 2) {
+    delete pl;
+    return evc_set_error(EVC_ERR_INVALID, "stride must be 1 or 2");
+  }
+  p.stride = cs;
   int total_kb = 0;
   long long ktot = 0;
   for (int s = 0; s < d->n_seg; ++s) {
@@ -462,7 +481,7 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
       delete pl;
       return evc_set_error(EVC_ERR_INVALID, "taps must be 1 or 9");
     }
-    if (a.ptr == nullptr || (a.C % 8) != 0 || a.C < 8 || a.W != d->W || a.H != d->H || a.B != d->B) {
+    if (a.ptr == nullptr || (a.C % 8) != 0 || a.C < 8 || a.W != d->W * cs || a.H != d->H * cs || a.B != d->B) {
       delete pl;
       return evc_set_error(EVC_ERR_INVALID, "A segment: C % 8 != 0 or extent mismatch");
     }
@@ -472,8 +491,8 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     }
     uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
     uint64_t strides[3] = {(uint64_t)a.stride_w * 2, (uint64_t)a.stride_h * 2, (uint64_t)a.stride_b * 2};
-    uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TB};
-    int rc = encode_map(&p.a_map[s], a.ptr, 4, dims, strides, box);
+    uint32_t box[4] = {64, (uint32_t)(TW * cs), (uint32_t)(TH * cs), (uint32_t)TB};
+    int rc = encode_map(&p.a_map[s], a.ptr, 4, dims, strides, box, cs);
     if (rc != EVC_OK) {
       delete pl;
       return rc;

@@ -28,7 +28,7 @@ class GemmDesc(C.Structure):
                 ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("bn", C.c_int32),
                 ("out", C.c_void_p), ("out_mode", C.c_int32), ("out_ld", C.c_int64), ("out_bs", C.c_int64),
                 ("bias", C.c_void_p), ("resid", C.c_void_p), ("resid_ld", C.c_int64),
-                ("alpha", C.c_float), ("max_ctas", C.c_int32), ("stats", C.c_void_p)]
+                ("alpha", C.c_float), ("max_ctas", C.c_int32), ("stats", C.c_void_p), ("stride", C.c_int32)]
 
 
 class StepCoef(C.Structure):

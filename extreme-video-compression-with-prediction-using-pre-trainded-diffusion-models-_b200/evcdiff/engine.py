@@ -87,6 +87,7 @@ class EngineBase:
         self._keep = []
         self._stat_acts = []
         self._deferred = []
+        self.fixed_groups = None  # models/unet.py: always 32 groups; NCSN++: min(C//4, 32)
         self.ws_bytes = 256
 
     # ----------------------------------------------------------------- recording helpers
@@ -138,7 +139,7 @@ class EngineBase:
         if xb is not None:
             self.ensure_stats(xb)
         C = xa.C + (xb.C if xb is not None else 0)
-        groups = gn_groups(C)
+        groups = self.fixed_groups or gn_groups(C)
 
         def run(li):
             ops.gn_apply(xa.t, xa.C, xb.t if xb is not None else None, xb.C if xb is not None else 0, xa.B,
@@ -147,7 +148,7 @@ class EngineBase:
         self._op(run, "gn_apply", dict(bytes=out.t.numel() * 4))
 
     def gemm(self, segs, w, out_t, out_mode, out_ld, out_bs=0, bias=None, resid=None, alpha=1.0, bias_fn=None,
-             stats_of=None):
+             stats_of=None, stride=1):
         """stats_of: the Act being written; when given (and the tile geometry allows it) its GroupNorm statistics
         are accumulated by the GEMM epilogue and no separate gn_stats launch is recorded for it."""
         stats_t = None
@@ -155,11 +156,11 @@ class EngineBase:
             self.alloc_stats(stats_of)
             stats_t = ("deferred", stats_of)
         plan_args = dict(out_bs=out_bs, bias=bias, resid=resid.t if isinstance(resid, Act) else resid,
-                         resid_ld=(resid.C if isinstance(resid, Act) else 0), alpha=alpha)
+                         resid_ld=(resid.C if isinstance(resid, Act) else 0), alpha=alpha, stride=stride)
         if stats_t is not None:
             # the arena does not exist yet: create the plan in finalize()
             self._deferred.append((len(self.ops), [(a.t if isinstance(a, Act) else a, taps) for a, taps in segs], w,
-                                   out_t, out_mode, out_ld, plan_args, stats_of))
+                                   out_t, out_mode, out_ld, plan_args, stats_of, bias_fn))
             plan = None
             flops = 2.0 * out_t.shape[0] * stats_of.H * stats_of.W * w.shape[-2] * w.shape[-1]
             self.flops += flops
@@ -189,6 +190,55 @@ class EngineBase:
                  dict(bytes=(a.t.numel() + out.t.numel()) * 2))
         return out
 
+    def attn_core(self, x, ss, gn_eps, ws, bs, heads, out_alpha):
+        """out = out_alpha * (x + OUT(softmax(q k^T / sqrt(d)) v)) with q,k,v = 1x1 projections of GN(x).
+        ws/bs: [Wq, Wk, Wv, Wo] as (out, in) bf16 and fp32 biases.  Unfused round-1 attention: batched GEMMs with a
+        per-sample B operand (K, then V^T written by a transposed-store epilogue) + row softmax."""
+        dev = self.device
+        C, N, B = x.C, x.H * x.W, self.B
+        d = C // heads
+        if d % 8 != 0:
+            raise EvcError("attention head dim must be a multiple of 8")
+        self._keep += [ss] + list(ws) + list(bs)
+        wq, wk, wv, wo = ws
+        bq, bk, bv, bo = bs
+        hn = self.new_act(x.H, x.W, C)
+        self.gn_apply(x, None, lambda li: ss, gn_eps, False, False, hn)
+        qk = self.pool.get((B, x.H, x.W, 2 * C))
+        self.gemm([(hn, 1)], torch.cat([wq, wk], 0).contiguous(), qk, EVC_OUT_BF16_ROWS, 2 * C,
+                  bias=torch.cat([bq, bk]).contiguous())
+        # key axis padded to a multiple of 8 (16-byte TMA strides); only toy shapes (N < 8) ever pad.  Pad columns:
+        # S = -inf (never written by the GEMM, so softmax gives P = 0) and V^T = 0.
+        Np = max(8, (N + 7) // 8 * 8)
+        if Np == N:
+            vT = self.pool.get((B, C, N))
+            S = self.pool.get((B, N, N), torch.float32)
+            Pm = self.pool.get((B, N, N))
+        else:
+            vT = torch.zeros((B, C, Np), dtype=torch.bfloat16, device=dev)
+            S = torch.full((B, N, Np), float("-inf"), dtype=torch.float32, device=dev)
+            Pm = torch.zeros((B, N, Np), dtype=torch.bfloat16, device=dev)
+        self.gemm([(hn, 1)], wv, vT, EVC_OUT_BF16_T, Np, out_bs=C * Np, bias=bv)
+        o = self.new_act(x.H, x.W, C)
+        qk3 = qk.view(B, N, 2 * C)
+        o3 = o.t.view(B, N, C)
+        for hd in range(heads):
+            q = qk3[:, :, hd * d:(hd + 1) * d].unsqueeze(1)  # (B,1,N,d)
+            k = qk3[:, :, C + hd * d:C + (hd + 1) * d]  # (B,N,d)  per-sample B operand
+            self.gemm([(q, 1)], k, S, EVC_OUT_F32_ROWS, Np, alpha=float(int(d) ** (-0.5)))
+            self._op(lambda li, S=S, Pm=Pm: ops.softmax_rows(S, Pm, B * N, Np), "softmax",
+                     dict(bytes=B * N * Np * 6))
+            self.gemm([(Pm.view(B, 1, N, Np), 1)], vT[:, hd * d:(hd + 1) * d, :], o3[:, :, hd * d:], EVC_OUT_BF16_ROWS, C)
+        out = self.new_act(x.H, x.W, C, scratch=False)
+        self.gemm([(o, 1)], wo, out.t, EVC_OUT_BF16_ROWS, C, bias=bo, resid=x, alpha=out_alpha, stats_of=out)
+        self.pool.put(qk)
+        if Np == N:
+            self.pool.put(vT); self.pool.put(S); self.pool.put(Pm)
+        else:
+            self._keep += [vT, S, Pm]
+        self.release(hn, o)
+        return out
+
     # ----------------------------------------------------------------- execution
     def finalize(self):
         self.stats_arena = torch.zeros(max(self.stats_total, 2), dtype=torch.int64, device=self.device)
@@ -196,9 +246,12 @@ class EngineBase:
         for a in self._stat_acts:
             _, off, n = a.stats
             a.stats = self.stats_arena[off:off + n]
-        for idx, segs, w, out_t, out_mode, out_ld, plan_args, act in self._deferred:
+        for idx, segs, w, out_t, out_mode, out_ld, plan_args, act, bias_fn in self._deferred:
             plan = ops.GemmPlan(segs, w, out_t, out_mode, out_ld, stats=act.stats, **plan_args)
-            self.ops[idx] = (lambda li, plan=plan: plan.launch())
+            if bias_fn is None:
+                self.ops[idx] = (lambda li, plan=plan: plan.launch())
+            else:
+                self.ops[idx] = (lambda li, plan=plan, bf=bias_fn: plan.launch(bf(li)))
         self._deferred = []
 
     def forward(self, label_idx=0):
@@ -385,53 +438,13 @@ class NCSNppEngine(EngineBase):
     def attn_block(self, i, s, x):
         """AttnBlockpp (layerspp.py:230-249): GN(affine, eps 1e-6) -> q,k,v NIN -> softmax(q k^T / sqrt(d)) v -> NIN_3."""
         sd, P, dev = self.sd, self.P, self.device
-        C, N, B = x.C, x.H * x.W, self.B
+        C = x.C
         heads = 1 if (self.head_ch == -1 or C < self.head_ch) else C // self.head_ch
-        d = C // heads
-        if d % 8 != 0:
-            raise EvcError("attention head dim must be a multiple of 8")
         ss = torch.cat([sd[P(i) + ".GroupNorm_0.weight"].float(), sd[P(i) + ".GroupNorm_0.bias"].float()]).to(dev)
-        ss = ss.contiguous()
-        self._keep.append(ss)
-        hn = self.new_act(x.H, x.W, C)
-        self.gn_apply(x, None, lambda li: ss, 1e-6, False, False, hn)
         # NIN: y = x @ W + b with W (in, out) -> GEMM weight rows = outputs
-        wq, wk, wv, wo = [sd[P(i) + f".NIN_{j}.W"].to(dev).t().to(torch.bfloat16) for j in range(4)]
-        bq, bk, bv, bo = [sd[P(i) + f".NIN_{j}.b"].float().to(dev) for j in range(4)]
-        qk = self.pool.get((B, x.H, x.W, 2 * C))
-        self.gemm([(hn, 1)], torch.cat([wq, wk], 0).contiguous(), qk, EVC_OUT_BF16_ROWS, 2 * C,
-                  bias=torch.cat([bq, bk]).contiguous())
-        # key axis padded to a multiple of 8 (16-byte TMA strides); only toy shapes (N < 8) ever pad.  Pad columns:
-        # S = -inf (never written by the GEMM, so softmax gives P = 0) and V^T = 0.
-        Np = max(8, (N + 7) // 8 * 8)
-        if Np == N:
-            vT = self.pool.get((B, C, N))
-            S = self.pool.get((B, N, N), torch.float32)
-            Pm = self.pool.get((B, N, N))
-        else:
-            vT = torch.zeros((B, C, Np), dtype=torch.bfloat16, device=dev)
-            S = torch.full((B, N, Np), float("-inf"), dtype=torch.float32, device=dev)
-            Pm = torch.zeros((B, N, Np), dtype=torch.bfloat16, device=dev)
-        self.gemm([(hn, 1)], wv.contiguous(), vT, EVC_OUT_BF16_T, Np, out_bs=C * Np, bias=bv.contiguous())
-        o = self.new_act(x.H, x.W, C)
-        qk3 = qk.view(B, N, 2 * C)
-        o3 = o.t.view(B, N, C)
-        for hd in range(heads):
-            q = qk3[:, :, hd * d:(hd + 1) * d].unsqueeze(1)  # (B,1,N,d)
-            k = qk3[:, :, C + hd * d:C + (hd + 1) * d]  # (B,N,d)  per-sample B operand
-            self.gemm([(q, 1)], k, S, EVC_OUT_F32_ROWS, Np, alpha=float(int(d) ** (-0.5)))
-            self._op(lambda li, S=S, Pm=Pm: ops.softmax_rows(S, Pm, B * N, Np), "softmax",
-                     dict(bytes=B * N * Np * 6))
-            self.gemm([(Pm.view(B, 1, N, Np), 1)], vT[:, hd * d:(hd + 1) * d, :], o3[:, :, hd * d:], EVC_OUT_BF16_ROWS, C)
-        out = self.new_act(x.H, x.W, C, scratch=False)
-        self.gemm([(o, 1)], wo.contiguous(), out.t, EVC_OUT_BF16_ROWS, C, bias=bo.contiguous(), resid=x, alpha=RSQRT2,
-                  stats_of=out)
-        self.pool.put(qk)
-        if Np == N:
-            self.pool.put(vT); self.pool.put(S); self.pool.put(Pm)
-        else:
-            self._keep += [vT, S, Pm]
-        self.release(hn, o)
+        ws = [sd[P(i) + f".NIN_{j}.W"].to(dev).t().to(torch.bfloat16).contiguous() for j in range(4)]
+        bs = [sd[P(i) + f".NIN_{j}.b"].float().to(dev).contiguous() for j in range(4)]
+        out = self.attn_core(x, ss.contiguous(), 1e-6, ws, bs, heads, RSQRT2)
         self.taps[f"m{i}"] = out
         return out
 

@@ -27,12 +27,14 @@ class GemmPlan:
     """
 
     def __init__(self, segs, w, out, out_mode, out_ld, out_bs=0, bias=None, resid=None, resid_ld=0, alpha=1.0,
-                 bn=None, max_ctas=0, stats=None):
+                 bn=None, max_ctas=0, stats=None, stride=1):
         lib = load()
         _require_cuda(w, out, bias, resid, *[s[0] for s in segs])
         d = GemmDesc()
         d.n_seg = len(segs)
         B, H, W_, _ = segs[0][0].shape
+        H, W_ = H // stride, W_ // stride
+        d.stride = stride
         ktot = 0
         for i, (a, taps) in enumerate(segs):
             assert a.dtype == torch.bfloat16 and a.dim() == 4 and a.stride(3) == 1, "A segment must be (B,H,W,C) bf16"

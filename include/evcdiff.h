@@ -49,7 +49,7 @@ int64_t evc_launch_count(void);
  *   out[b, y, x, n] = alpha * ( sum_seg sum_tap sum_c  A_seg[b, y+dy, x+dx, c] * Wt[zb, n, k(seg,tap,c)]
  *                               + bias[n] + resid[b, y, x, n] )
  *
- * A segments: up to 3 bf16 tensors viewed as (B, H, W, C) with element strides; taps = 1 (1x1 / GEMM)
+ * A segments: up to 3 bf16 tensors viewed as (B, H, W, C) (or (B, 2H, 2W, C) with stride 2) with element strides; taps = 1 (1x1 / GEMM)
  * or 9 (3x3, zero padding 1).  C must be a multiple of 8 (64 for full tensor-core efficiency).  Several segments implement a virtual
  * channel concat and the fused 1x1 skip branch of a residual block (extra K).
  * Wt: bf16 (w_batches, N, K_total), K contiguous, K order = segment-major, tap-major, channel-minor.
@@ -92,6 +92,9 @@ typedef struct evc_gemm_desc {
    * stats[(b*N + n)*2 + {0,1}] += {sum, sum of squares} * 2^20 as 64-bit integers (order-independent, hence
    * deterministic); the caller zeroes the buffer before the launch.  Same format as evc_gn_stats. */
   int64_t* stats;
+  /* convolution stride, 0/1 or 2 (models/unet.py:219 down-sampling conv): every A segment then has extent
+   * (B, stride*H, stride*W, C) and tap (dy,dx) reads input pixel (stride*y + dy, stride*x + dx). */
+  int32_t stride;
 } evc_gemm_desc;
 
 typedef struct evc_gemm_plan evc_gemm_plan;

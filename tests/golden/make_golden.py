@@ -98,7 +98,46 @@ def run_samplers(net, cfg, tag, out, B, sub_ddpm, sub_ddim, sub_pndm, seed):
     out[f"{tag}_fpndm{sub_pndm}_labels"] = np.array(labels, dtype=np.float64)
 
 
+def make_unet_plain():
+    """models/unet.py UNet_DDPM (BASELINE config 5 variant): 'deep' and 'deeper' at a toy size."""
+    from models.unet import UNet_DDPM
+    from oracle import unet_plain as U
+    out = {}
+    for mode in ("deep", "deeper"):
+        cfg = common.make_config(ngf=32, image_size=16)
+        cfg.mode = mode
+        net = UNet_DDPM(cfg).eval()
+        shapes = U.unet_param_shapes(cfg)
+        sd = common.seeded_state_dict(shapes, seed=21, active=True)
+        full = dict(net.state_dict())
+        assert [k for k in full if k not in ("betas", "alphas", "alphas_prev")] == list(sd.keys()), mode
+        full.update(sd)
+        net.load_state_dict(full, strict=True)
+        g = torch.Generator().manual_seed(22)
+        x = torch.randn(2, 15, 16, 16, generator=g)
+        # fp32: unlike NCSNpp (ncsnpp_more.py:293) models/unet.py never casts, a float64 cond crashes its first conv
+        cond = torch.rand(2, 6, 16, 16, generator=g) * 2 - 1
+        out[f"{mode}_x"], out[f"{mode}_cond"] = x.numpy(), cond.numpy()
+        for lab in (0, 990):
+            with torch.no_grad():
+                out[f"{mode}_eps_{lab}"] = net(x, torch.full((2,), lab, dtype=torch.long), cond=cond).numpy()
+        orig = torch.randn_like
+        tape = NoiseTape(23)
+        torch.randn_like = tape
+        try:
+            y = ref_models.ddpm_sampler(x.clone(), net, cond=cond, final_only=True, denoise=True, subsample_steps=10,
+                                        clip_before=True, verbose=True, log=True)
+        finally:
+            torch.randn_like = orig
+        out[f"{mode}_ddpm10"] = y.numpy()
+    np.savez_compressed(os.path.join(HERE, "unet_plain.npz"), **out)
+    print("wrote unet_plain.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB raw")
+
+
 def main():
+    if "--unet-plain-only" in sys.argv:
+        return make_unet_plain()
+    make_unet_plain()
     out = {}
     # ---- schedule + embedding + FIR (config independent pieces)
     cfg = common.tiny_config()

@@ -109,3 +109,20 @@ def test_get_sigmas_and_coefficients():
     assert list(steps) == list(range(0, 1000, 10)) and torch.equal(a, a2) and torch.equal(ap, ap2) and torch.equal(b, b2)
     steps, a, ap, b = M._subsampled_schedule(net, 1000)
     assert len(steps) == 1000 and torch.equal(b, net.betas)
+
+
+def test_plain_unet_state_dict_matches_reference_layout():
+    from evcdiff.models.unet import UNet_DDPM, unet_spec
+    from oracle import unet_plain as U
+    for mode in ("deep", "deeper"):
+        cfg = common.make_config(ngf=32, image_size=16)
+        cfg.mode = mode
+        net = UNet_DDPM(cfg)
+        sd = net.state_dict()
+        shapes = U.unet_param_shapes(cfg)
+        keys = [k for k in sd if k not in ("betas", "alphas", "alphas_prev")]
+        assert keys == list(shapes.keys())
+        assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in keys)
+        ours, theirs = unet_spec(cfg), U.unet_spec(cfg)
+        assert ours["down"] == theirs["down"] and ours["mid"] == theirs["mid"] and ours["up"] == theirs["up"]
+        assert float(sd["unet.out.weight"].abs().max()) < 1e-4  # zero-init output conv (unet.py:243)

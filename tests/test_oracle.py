@@ -141,3 +141,27 @@ def test_param_inventory_full():
     assert shapes["unet.all_modules.3.actnorm0.Dense_0.weight"] == (384, 768)
     full = dict(np.load(os.path.join(G, "ncsnpp_full.npz")))
     assert int(full["n_params"]) == n
+
+
+@pytest.mark.parametrize("mode", ["deep", "deeper"])
+def test_unet_plain(mode):
+    """models/unet.py variant (BASELINE config 5): eps and a DDPM-10 trajectory against the reference goldens."""
+    from oracle import unet_plain as U
+    g = dict(np.load(os.path.join(G, "unet_plain.npz")))
+    cfg = common.make_config(ngf=32, image_size=16)
+    cfg.mode = mode
+    sd = common.seeded_state_dict(U.unet_param_shapes(cfg), seed=21, active=True)
+    x, cond = T(g[f"{mode}_x"]), T(g[f"{mode}_cond"])
+    for lab in (0, 990):
+        e = U.unet_forward(sd, cfg, x, torch.full((2,), lab, dtype=torch.long), cond)
+        assert common.rel_l2(e, T(g[f"{mode}_eps_{lab}"])) < 1e-5
+    tape = _tape(23, 9, x.shape)
+    model = lambda xx, yy: U.unet_forward(sd, cfg, xx, yy, cond)
+    y = S.ddpm_sampler(x.clone(), model, S.schedule(cfg), lambda i: tape[i], subsample_steps=10)
+    assert common.rel_l2(y.unsqueeze(0), T(g[f"{mode}_ddpm10"])) < 1e-4
+    full = common.full_config()
+    full.mode = mode
+    shapes = U.unet_param_shapes(full)
+    n = sum(int(np.prod(s)) for s in shapes.values())
+    # ngf=192: 'deep' 80.4 M parameters in 328 tensors (+3 buffers = 331), 'deeper' 240.9 M (SURVEY.md 8a V1)
+    assert (n, len(shapes)) == ((80_434_575, 328) if mode == "deep" else (240_926_991, 390))
