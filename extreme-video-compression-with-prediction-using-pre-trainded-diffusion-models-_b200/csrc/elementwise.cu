@@ -20,7 +20,16 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   u.w = pack_bf16x2(f[6], f[7]);
   return u;
 }
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// x * sigmoid(x) with two MUFU ops (ex2, rcp) and no range fix-up code: exp(-x) = 2^(-x*log2(e)); for x -> -inf the
+// product is x * rcp(inf) = -0, for x -> +inf it is x * rcp(1) = x.
+__device__ __forceinline__ float silu_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return x * r;
+}
+// read-only 16-byte load that allocates in L1 (FIR stencils: every input vector is re-read by 4-9 neighbouring threads)
+__device__ __forceinline__ uint4 ld_ro16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 // streaming 16-byte load (read once: do not pollute L1)
 __device__ __forceinline__ uint4 ld_nc16(const void* p) {
   uint4 r;
@@ -127,36 +136,47 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
 // registers) and streams pixels with 4 independent 16-byte loads in flight.  Group statistics are rebuilt per
 // block from the per-channel sums: one warp per group, shuffle tree (deterministic).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
+template <bool SILU>
+__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
                                                        const __nv_bfloat16* __restrict__ x1, int C1, int HW,
                                                        const long long* __restrict__ stats0,
                                                        const long long* __restrict__ stats1, int groups, float eps,
-                                                       const float* __restrict__ ss, int adagn, int silu,
+                                                       const float* __restrict__ ss, int adagn,
                                                        __nv_bfloat16* __restrict__ y, int pix_per_block) {
   __shared__ float s_mean[64], s_rstd[64];
+  __shared__ float s_ps[64][9], s_pq[64][9];
   const int C = C0 + C1;
   const int b = blockIdx.y;
   const int cpg = C / groups;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int nthr = blockDim.x * blockDim.y;
-  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
   const float inv_n = 1.f / ((float)cpg * (float)HW);
-  for (int g = warp; g < groups; g += nwarps) {
+  // group statistics from the per-channel sums: `per` threads per group, partials combined in a fixed order
+  int per = nthr / groups;
+  per = per < 1 ? 1 : (per > 8 ? 8 : per);
+  for (int t = tid; t < groups * per; t += nthr) {
+    const int g = t / per, k = t % per;
     float s = 0.f, q = 0.f;
-    for (int j = lane; j < cpg; j += 32) {
+    for (int j = k; j < cpg; j += per) {
       const int cc = g * cpg + j;
       const long long* st = (cc < C0) ? stats0 + ((long long)b * C0 + cc) * 2 : stats1 + ((long long)b * C1 + (cc - C0)) * 2;
       s += (float)((double)st[0] * (1.0 / 1048576.0));
       q += (float)((double)st[1] * (1.0 / 1048576.0));
     }
-    s = warp_sum(s);
-    q = warp_sum(q);
-    if (lane == 0) {
-      const float mean = s * inv_n;
-      const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-      s_mean[g] = mean;
-      s_rstd[g] = rsqrtf(var + eps);
+    s_ps[g][k] = s;
+    s_pq[g][k] = q;
+  }
+  __syncthreads();
+  for (int g = tid; g < groups; g += nthr) {
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < per; ++k) {
+      s += s_ps[g][k];
+      q += s_pq[g][k];
     }
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + eps);
   }
   __syncthreads();
   const int v = threadIdx.x;  // channel vector
@@ -170,18 +190,19 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const __nv_bfloat16* __r
     bb[j] = ss[C + c + j] - s_mean[g] * a[j];
   }
   const bool first = (c < C0);
-  const __nv_bfloat16* src = first ? x0 + c : x1 + (c - C0);
   const int ld = first ? C0 : C1;
-  src += (long long)b * HW * ld;
-  __nv_bfloat16* dst = y + (long long)b * HW * C + c;
   const int rows = blockDim.y;
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(HW, p_begin + pix_per_block);
-  int p = p_begin + threadIdx.y;
-  for (; p + 3 * rows < p_end; p += 4 * rows) {
+  const int p0 = p_begin + threadIdx.y;
+  const __nv_bfloat16* src = (first ? x0 + c : x1 + (c - C0)) + ((long long)b * HW + p0) * ld;
+  __nv_bfloat16* dst = y + ((long long)b * HW + p0) * C + c;
+  const long long sstep = (long long)rows * ld, dstep = (long long)rows * C;
+  int n = (p0 < p_end) ? (p_end - p0 + rows - 1) / rows : 0;  // pixels this thread handles
+  for (; n >= 4; n -= 4) {
     uint4 u[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = ld_nc16(src + (long long)(p + k * rows) * ld);
+    for (int k = 0; k < 4; ++k) u[k] = ld_nc16(src + k * sstep);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float f[8];
@@ -189,20 +210,24 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const __nv_bfloat16* __r
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float t = fmaf(f[j], a[j], bb[j]);
-        f[j] = silu ? silu_f(t) : t;
+        f[j] = SILU ? silu_f(t) : t;
       }
-      *reinterpret_cast<uint4*>(dst + (long long)(p + k * rows) * C) = pack8(f);
+      *reinterpret_cast<uint4*>(dst + k * dstep) = pack8(f);
     }
+    src += 4 * sstep;
+    dst += 4 * dstep;
   }
-  for (; p < p_end; p += rows) {
+  for (; n > 0; --n) {
     float f[8];
-    unpack8(ld_nc16(src + (long long)p * ld), f);
+    unpack8(ld_nc16(src), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float t = fmaf(f[j], a[j], bb[j]);
-      f[j] = silu ? silu_f(t) : t;
+      f[j] = SILU ? silu_f(t) : t;
     }
-    *reinterpret_cast<uint4*>(dst + (long long)p * C) = pack8(f);
+    *reinterpret_cast<uint4*>(dst) = pack8(f);
+    src += sstep;
+    dst += dstep;
   }
 }
 
@@ -238,13 +263,13 @@ __global__ void fir_up_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
       }
       const __nv_bfloat16* row = xb + (long long)yy * W * C;
       float c0[8], cm[8], cp[8];
-      unpack8(ld_nc16(row + (long long)ix * C), c0);
-      if (ix > 0) unpack8(ld_nc16(row + (long long)(ix - 1) * C), cm);
+      unpack8(ld_ro16(row + (long long)ix * C), c0);
+      if (ix > 0) unpack8(ld_ro16(row + (long long)(ix - 1) * C), cm);
       else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) cm[j] = 0.f;
       }
-      if (ix + 1 < W) unpack8(ld_nc16(row + (long long)(ix + 1) * C), cp);
+      if (ix + 1 < W) unpack8(ld_ro16(row + (long long)(ix + 1) * C), cp);
       else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) cp[j] = 0.f;
@@ -298,7 +323,7 @@ __global__ void fir_down_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
         const int xx = 2 * ox - 1 + c;
         if (xx < 0 || xx >= W) continue;
         const float w = k[a] * k[c];
-        const uint4 u = ld_nc16(xb + ((long long)yy * W + xx) * C);
+        const uint4 u = ld_ro16(xb + ((long long)yy * W + xx) * C);
         float f[8];
         unpack8(u, f);
 #pragma unroll
@@ -449,14 +474,8 @@ extern "C" int evc_gn_apply(const void* x0, int32_t C0, const void* x1, int32_t 
   const int C = C0 + C1;
   const int nvec = C / 8;
   if (nvec > 256 || groups > 64) return evc_set_error(EVC_ERR_INVALID, "evc_gn_apply: C > 2048 or groups > 64");
-  // (block = nvec x rows threads <= 1024: rows <= 4 whenever nvec > 32 because nvec*rows is rounded to whole warps)
-  // whole warps only (the group statistics use warp shuffles): rows is a multiple of 32 / gcd(nvec, 32)
-  int g32 = 32, t = nvec;
-  while (t) { const int r2 = g32 % t; g32 = t; t = r2; }
-  const int step = 32 / g32;
-  int rows = (256 / nvec) / step * step;
-  if (rows < step) rows = step;
-  if (nvec * rows > 1024) return evc_set_error(EVC_ERR_INVALID, "evc_gn_apply: unsupported channel count");
+  int rows = 256 / nvec;
+  if (rows < 1) rows = 1;
   const int sms = evc_num_sms();
   int chunks = (sms * 6 + B - 1) / B;
   const int max_chunks = (HW + rows - 1) / rows;
@@ -465,9 +484,16 @@ extern "C" int evc_gn_apply(const void* x0, int32_t C0, const void* x1, int32_t 
   const int ppb = (HW + chunks - 1) / chunks;
   chunks = (HW + ppb - 1) / ppb;
   dim3 grid(chunks, B), block(nvec, rows);
-  gn_apply_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1, HW, reinterpret_cast<const long long*>(stats0),
-      reinterpret_cast<const long long*>(stats1), groups, eps, ss, adagn, silu, reinterpret_cast<__nv_bfloat16*>(y), ppb);
+  if (silu)
+    gn_apply_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1, HW,
+        reinterpret_cast<const long long*>(stats0), reinterpret_cast<const long long*>(stats1), groups, eps, ss, adagn,
+        reinterpret_cast<__nv_bfloat16*>(y), ppb);
+  else
+    gn_apply_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1, HW,
+        reinterpret_cast<const long long*>(stats0), reinterpret_cast<const long long*>(stats1), groups, eps, ss, adagn,
+        reinterpret_cast<__nv_bfloat16*>(y), ppb);
   return evc_check_launch("gn_apply_kernel");
 }
 

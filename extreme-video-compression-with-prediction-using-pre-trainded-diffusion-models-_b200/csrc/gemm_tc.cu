@@ -50,11 +50,15 @@ struct alignas(64) GemmParams {
   int stats_combine;  // 1: the four epilogue warps of a tile belong to one sample (TW*TH == 128)
   int sample_rows;    // TW*TH
   int stride;         // convolution stride (1 or 2): input coordinate = stride * output coordinate + tap offset
+  int m_tiles;        // tiles_x * tiles_y * tiles_b
 };
 
-__device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int& x0, int& y0, int& b0, int& n0) {
+// Work unit `tile` of a CTA (CG = 1) or CTA pair (CG = 2): N tile tn = tile % tiles_n, M tile(s) CG*(tile/tiles_n)+rank.
+template <int CG>
+__device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int rank, int& x0, int& y0, int& b0,
+                                            int& n0) {
   int tn = tile % p.tiles_n;
-  int tm = tile / p.tiles_n;
+  int tm = (tile / p.tiles_n) * CG + rank;  // may be == m_tiles for the peer of the last pair: fully out of range
   int tx = tm % p.tiles_x;
   int t2 = tm / p.tiles_x;
   int ty = t2 % p.tiles_y;
@@ -133,12 +137,16 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, const float (&f
   }
 }
 
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
+  const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;  // 0 = leader (issues the MMAs)
+  const int unit = blockIdx.x / CG;
+  const int num_units = gridDim.x / CG;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.BN / CG) * 128u;  // each CTA of a pair stages half of the B tile
   const uint32_t stage_bytes = kABytes + b_bytes;
   const uint32_t bar_base = base + p.num_stages * stage_bytes;
   // barrier slots (8 B each): full[8] | empty[8] | tmem_full[2] | tmem_empty[2] | tmem base slot
@@ -154,32 +162,38 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), CG);  // one arrival per producing CTA (the leader's barrier collects both)
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiThreads);
+      mbar_init(tempty_bar(s), CG * (kEpiThreads / 32));  // one arrival per epilogue warp of every CTA
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  if (CG == 2) cluster_sync_all();  // peer barriers initialised before anyone signals them; both CTAs alive
+  if (warp == 2) {
+    if (CG == 2) tmem_alloc_2sm(tmem_slot, kTmemCols);
+    else tmem_alloc(tmem_slot, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+  const int m_pairs = (p.m_tiles + CG - 1) / CG;
+  const int total_tiles = m_pairs * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < total_tiles; tile += num_units) {
       int x0, y0, b0, n0;
-      decode_tile(p, tile, x0, y0, b0, n0);
+      decode_tile<CG>(p, tile, rank, x0, y0, b0, n0);
       const int zb = p.b_batched ? b0 : 0;
+      const int nb = n0 + rank * (p.BN / CG);  // this CTA's half of the B tile
       int kbase = 0;
       for (int s = 0; s < p.n_seg; ++s) {
         const int taps = p.seg_taps[s];
@@ -189,10 +203,18 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           const int dx = (taps == 9) ? (t % 3 - 1) : 0;
           for (int c = 0; c < p.seg_kb[s]; ++c) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), p.tx_bytes);
             const uint32_t sa = base + stage * stage_bytes;
-            tma_load_4d(&p.a_map[s], sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
-            tma_load_3d(&p.b_map, sa + kABytes, full_bar(stage), ktap + c * 64, n0, zb);
+            if (CG == 2) {
+              // both CTAs' bytes land on the leader's barrier; the peer contributes a plain (remote) arrival
+              if (rank == 0) mbar_expect_tx(full_bar(stage), p.tx_bytes * 2u);
+              else mbar_arrive_cluster(full_bar(stage), 0);
+              tma_load_4d_2sm(&p.a_map[s], sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
+              tma_load_3d_2sm(&p.b_map, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
+            } else {
+              mbar_expect_tx(full_bar(stage), p.tx_bytes);
+              tma_load_4d(&p.a_map[s], sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
+              tma_load_3d(&p.b_map, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
+            }
             if (++stage == p.num_stages) {
               stage = 0;
               phase ^= 1u;
@@ -202,13 +224,13 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         kbase += taps * p.seg_c[s];
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.BN));
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    const uint32_t idesc = umma_idesc_bf16(128u * CG, static_cast<uint32_t>(p.BN));
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -223,10 +245,16 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-          umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (CG == 2) umma_bf16_2sm(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          else umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(empty_bar(stage));
-        if (kb == p.total_kb - 1) umma_commit(tfull_bar(acc));
+        if (CG == 2) {
+          umma_commit_2sm(empty_bar(stage), 3);  // frees this stage in both CTAs
+          if (kb == p.total_kb - 1) umma_commit_2sm(tfull_bar(acc), 3);
+        } else {
+          umma_commit(empty_bar(stage));
+          if (kb == p.total_kb - 1) umma_commit(tfull_bar(acc));
+        }
         if (++stage == p.num_stages) {
           stage = 0;
           phase ^= 1u;
@@ -254,11 +282,11 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     // [4 warps][BN][2] floats, after the residual rows
     float* sstat = reinterpret_cast<float*>(gsm + (bar_base - base) + 256 + 1024 + (p.resid_smem ? 128u * res_pitch : 0u));
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       int x0, y0, b0, n0;
-      decode_tile(p, tile, x0, y0, b0, n0);
+      decode_tile<CG>(p, tile, rank, x0, y0, b0, n0);
       const int b = b0 + db;
       const bool valid = (row < p.rows_valid) && (b < p.B);
       const long long pin = (long long)(y0 + dy) * p.W + (x0 + dx);
@@ -298,7 +326,11 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           released = true;
           // last TMEM read of this tile is complete: hand the accumulator stage back to the MMA warp
           tc_fence_before();
-          mbar_arrive(tempty_bar(acc));
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+            else mbar_arrive(tempty_bar(acc));
+          }
         }
         const int n = n0 + c0;
         float f[32];
@@ -370,7 +402,11 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       }
       if (!released) {  // this warp had no chunk in this tile (BN <= 32 and grp == 1)
         tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+          else mbar_arrive(tempty_bar(acc));
+        }
       }
       if (p.stats != nullptr && p.stats_combine) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -389,9 +425,11 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading its B half
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -402,6 +440,7 @@ using namespace evc;
 
 struct evc_gemm_plan {
   GemmParams p;
+  int cg;  // 1: one CTA per 128-row tile; 2: CTA pair (cta_group::2), 256-row tile, B tile split across the pair
   int grid;
   int smem_bytes;
   double flops;
@@ -466,6 +505,26 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   p.BN = d->bn;
   p.N = d->w_rows;
   p.tiles_n = (d->w_rows + d->bn - 1) / d->bn;
+  p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  // CTA pairs pay off when there are enough 256-row tiles to fill the 74 SM pairs; they need a shared B operand and
+  // an N tile that splits into two halves of whole 8-row swizzle atoms.
+  int cg = 1;
+  {
+    const bool can_pair = !p.b_batched && (d->bn % 32) == 0 && d->bn >= 64 && (d->w_rows % d->bn) == 0;
+    if (d->cta_group == 2) {
+      if (!can_pair) {
+        delete pl;
+        return evc_set_error(EVC_ERR_INVALID, "cta_group 2 needs shared weights, bn % 32 == 0, bn >= 64, N % bn == 0");
+      }
+      cg = 2;
+    } else if (d->cta_group == 0 && can_pair) {
+      // same-box A/B on B200 under the 1 kW cap (profiles/r01_notes.md): pairs are ~1.5 % faster end to end --
+      // fewer B-tile bytes per FLOP lowers power, which raises the sustained clock
+      const long long pair_tiles = (long long)((p.m_tiles + 1) / 2) * p.tiles_n;
+      if (pair_tiles >= 2LL * (evc_num_sms() / 2)) cg = 2;
+    }
+  }
+  pl->cg = cg;
 
   const int cs = d->stride <= 1 ? 1 : d->stride;
   if (cs != 1 && cs != 2) {
@@ -517,7 +576,7 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     uint64_t bstride = d->w_batches > 1 ? (uint64_t)d->w_batch_stride * 2 : (uint64_t)d->w_row_stride * 2 * d->w_rows;
     if (bstride % 16) bstride = ((bstride + 15) / 16) * 16;
     uint64_t strides[2] = {(uint64_t)d->w_row_stride * 2, bstride};
-    uint32_t box[3] = {64, (uint32_t)d->bn, 1};
+    uint32_t box[3] = {64, (uint32_t)(d->bn / cg), 1};
     int rc = encode_map(&p.b_map, d->w, 3, dims, strides, box);
     if (rc != EVC_OK) {
       delete pl;
@@ -533,9 +592,9 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   p.resid_ld = d->resid_ld;
   p.alpha = d->alpha;
   const int a_box_bytes = 64 * 2 * p.rows_valid;
-  p.tx_bytes = (unsigned)(a_box_bytes + d->bn * 128);
+  p.tx_bytes = (unsigned)(a_box_bytes + (d->bn / cg) * 128);  // per CTA
 
-  const int stage_bytes = kABytes + d->bn * 128;
+  const int stage_bytes = kABytes + (d->bn / cg) * 128;
   // shared memory: [stages][barriers 256 B][bias 1 KB][residual rows 128 x (2*BN + 16) B, only with a residual]
   p.resid_smem = (d->resid != nullptr && (d->resid_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(d->resid) & 15) == 0 &&
                   (d->w_rows % 8) == 0) ? 1 : 0;
@@ -557,10 +616,11 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   p.num_stages = stages;
   pl->smem_bytes = stages * stage_bytes + 1024 + tail_bytes;
 
-  const long long tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+  const long long units = (long long)((p.m_tiles + cg - 1) / cg) * p.tiles_n;  // tiles (cg 1) or tile pairs (cg 2)
   int sms = evc_num_sms();
-  int cap = d->max_ctas > 0 ? d->max_ctas : sms;
-  pl->grid = (int)(tiles < cap ? tiles : cap);
+  int cap = (d->max_ctas > 0 ? d->max_ctas : sms) / cg;
+  if (cap < 1) cap = 1;
+  pl->grid = cg * (int)(units < cap ? units : cap);
   pl->flops = 2.0 * (double)d->B * d->H * d->W * (double)d->w_rows * (double)d->w_k;
   *out_plan = pl;
   return EVC_OK;
@@ -570,19 +630,41 @@ extern "C" int evc_gemm_plan_launch(const evc_gemm_plan* pl, const float* bias_o
   if (pl == nullptr) return evc_set_error(EVC_ERR_INVALID, "null plan");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(evc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(evc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(evc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
     attr_set = true;
   }
-  if (bias_override != nullptr) {
-    GemmParams p = pl->p;
-    p.bias = bias_override;
-    evc_gemm_kernel<<<pl->grid, kThreads, pl->smem_bytes, (cudaStream_t)stream>>>(p);
+  GemmParams p = pl->p;
+  if (bias_override != nullptr) p.bias = bias_override;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(pl->grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = pl->smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  cudaError_t e;
+  if (pl->cg == 2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, evc_gemm_kernel<2>, p);
   } else {
-    evc_gemm_kernel<<<pl->grid, kThreads, pl->smem_bytes, (cudaStream_t)stream>>>(pl->p);
+    e = cudaLaunchKernelEx(&cfg, evc_gemm_kernel<1>, p);
   }
-  return evc_check_launch("evc_gemm_kernel");
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
+  }
+  return evc_check_launch(pl->cg == 2 ? "evc_gemm_kernel<2>" : "evc_gemm_kernel<1>");
 }
+
+extern "C" int evc_gemm_plan_cta_group(const evc_gemm_plan* pl) { return pl ? pl->cg : 0; }
 
 extern "C" void evc_gemm_plan_destroy(evc_gemm_plan* pl) { delete pl; }
 extern "C" double evc_gemm_plan_flops(const evc_gemm_plan* pl) { return pl ? pl->flops : 0.0; }

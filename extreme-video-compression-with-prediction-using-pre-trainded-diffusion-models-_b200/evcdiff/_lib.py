@@ -28,7 +28,7 @@ class GemmDesc(C.Structure):
                 ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("bn", C.c_int32),
                 ("out", C.c_void_p), ("out_mode", C.c_int32), ("out_ld", C.c_int64), ("out_bs", C.c_int64),
                 ("bias", C.c_void_p), ("resid", C.c_void_p), ("resid_ld", C.c_int64),
-                ("alpha", C.c_float), ("max_ctas", C.c_int32), ("stats", C.c_void_p), ("stride", C.c_int32)]
+                ("alpha", C.c_float), ("max_ctas", C.c_int32), ("stats", C.c_void_p), ("stride", C.c_int32), ("cta_group", C.c_int32)]
 
 
 class StepCoef(C.Structure):
@@ -51,6 +51,7 @@ SIGNATURES = {
     "evc_gemm_plan_launch": (C.c_int, [_vp, _vp, _vp]),
     "evc_gemm_plan_destroy": (None, [_vp]),
     "evc_gemm_plan_flops": (C.c_double, [_vp]),
+    "evc_gemm_plan_cta_group": (C.c_int, [_vp]),
     "evc_gn_stats_workspace": (C.c_int, [_i32, _i32, _i32, C.POINTER(C.c_int64)]),
     "evc_gn_stats": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
     "evc_gn_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _vp, _i32, _i32, _vp, _vp]),

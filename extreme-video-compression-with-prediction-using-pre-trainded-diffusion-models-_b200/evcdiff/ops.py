@@ -1,5 +1,6 @@
 """Tensor-level wrappers over the C ABI.  torch is used for device memory and the current stream only."""
 import ctypes as C
+import os
 
 import torch
 
@@ -27,7 +28,7 @@ class GemmPlan:
     """
 
     def __init__(self, segs, w, out, out_mode, out_ld, out_bs=0, bias=None, resid=None, resid_ld=0, alpha=1.0,
-                 bn=None, max_ctas=0, stats=None, stride=1):
+                 bn=None, max_ctas=0, stats=None, stride=1, cta_group=None):
         lib = load()
         _require_cuda(w, out, bias, resid, *[s[0] for s in segs])
         d = GemmDesc()
@@ -69,6 +70,11 @@ class GemmPlan:
         d.resid_ld = resid_ld
         d.alpha = alpha
         d.max_ctas = max_ctas
+        if cta_group is None:
+            cta_group = int(os.environ.get("EVC_GEMM_CTA_GROUP", "0"))
+            if cta_group == 2 and (w.dim() == 3 or bn % 32 != 0 or bn < 64 or n % bn != 0):
+                cta_group = 1  # the env override only applies where pairing is possible
+        d.cta_group = cta_group
         if stats is not None:
             assert stats.dtype == torch.int64 and stats.is_cuda
             d.stats = stats.data_ptr()
@@ -78,6 +84,7 @@ class GemmPlan:
         check(lib.evc_gemm_plan_create(C.byref(d), C.byref(h)), "evc_gemm_plan_create")
         self._h = h
         self.flops = lib.evc_gemm_plan_flops(h)
+        self.cta_group = lib.evc_gemm_plan_cta_group(h)
 
     def launch(self, bias_override=None):
         check(self._lib.evc_gemm_plan_launch(self._h, _ptr(bias_override), stream_ptr()), "evc_gemm_plan_launch")

@@ -95,6 +95,9 @@ typedef struct evc_gemm_desc {
   /* convolution stride, 0/1 or 2 (models/unet.py:219 down-sampling conv): every A segment then has extent
    * (B, stride*H, stride*W, C) and tap (dy,dx) reads input pixel (stride*y + dy, stride*x + dx). */
   int32_t stride;
+  /* 0 = automatic, 1 = one CTA per 128-row tile, 2 = CTA pair (tcgen05 cta_group::2, 256-row tile; the pair shares
+   * one B tile, each CTA staging half of it).  2 needs shared weights, bn % 32 == 0, bn >= 64, N % bn == 0. */
+  int32_t cta_group;
 } evc_gemm_desc;
 
 typedef struct evc_gemm_plan evc_gemm_plan;
@@ -106,6 +109,8 @@ int evc_gemm_plan_launch(const evc_gemm_plan* plan, const float* bias_override, 
 void evc_gemm_plan_destroy(evc_gemm_plan* plan);
 /* 2 * M * N * K of one launch (dense FLOPs, for the roofline) */
 double evc_gemm_plan_flops(const evc_gemm_plan* plan);
+/* 1 or 2: the CTA grouping the plan selected */
+int evc_gemm_plan_cta_group(const evc_gemm_plan* plan);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm statistics and the fused normalise / AdaGN / affine / SiLU pass.

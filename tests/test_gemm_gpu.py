@@ -150,3 +150,4 @@ def test_fused_groupnorm_statistics(B, H, Cin, N, resid):
     plan.launch()
     torch.cuda.synchronize()
     assert torch.equal(s1, stats)  # integer atomics: bit-reproducible
+

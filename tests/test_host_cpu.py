@@ -126,3 +126,24 @@ def test_plain_unet_state_dict_matches_reference_layout():
         ours, theirs = unet_spec(cfg), U.unet_spec(cfg)
         assert ours["down"] == theirs["down"] and ours["mid"] == theirs["mid"] and ours["up"] == theirs["up"]
         assert float(sd["unet.out.weight"].abs().max()) < 1e-4  # zero-init output conv (unet.py:243)
+
+
+def test_checkpoint_loading_flow_like_city_sender():
+    """city_sender.py:304-324: DataParallel wrap, load `module.`-prefixed state, EMA shadow copy, unwrap."""
+    from evcdiff.models.better.ncsnpp_more import UNetMore_DDPM
+    from evcdiff.models.ema import EMAHelper
+    cfg = common.tiny_config()
+    src = UNetMore_DDPM(cfg)
+    states = [{"module." + k: v.clone() for k, v in src.state_dict().items()},
+              {k: torch.full_like(p, 0.25) for k, p in src.named_parameters()}]
+    scorenet = torch.nn.DataParallel(UNetMore_DDPM(cfg))
+    v0 = scorenet.module.unet._weights_version()
+    scorenet.load_state_dict(states[0], strict=False)
+    scorenet.eval()
+    ema_helper = EMAHelper(mu=cfg.model.ema_rate)
+    ema_helper.register(scorenet)
+    ema_helper.load_state_dict(states[-1])
+    ema_helper.ema(scorenet)
+    net = scorenet.module if hasattr(scorenet, "module") else scorenet
+    assert all(bool((p == 0.25).all()) for p in net.parameters())
+    assert net.unet._weights_version() != v0  # the engine will repack its operands

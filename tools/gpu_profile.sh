@@ -1,13 +1,15 @@
 #!/bin/bash
-# ncu evidence for profiles/: launch list (device time per launch) + one full capture of the dominant kernel.
+# ncu evidence for profiles/: launch list (device time per launch) + full captures of the dominant kernels.
 # Same command line plain first (must exit 0), then under ncu.
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
 $CMD > gpurun_out/plain.log 2> gpurun_out/plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 700 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
-$CMD > gpurun_out/plain2.log 2> gpurun_out/plain2.err &&
-ncu --set full --clock-control none --import-source on -k regex:evc_gemm_kernel -s 1 -c 3 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_full.log 2>&1
-echo "full capture rc=$?"
-ls -la gpurun_out/
-tail -3 gpurun_out/ncu_launches.log gpurun_out/ncu_full.log
+ncu --set full --clock-control none --import-source on -k regex:evc_gemm_kernel -s 1 -c 2 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
+echo "gemm capture rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:gn_apply_kernel -s 2 -c 2 -o gpurun_out/prof_gn_apply $CMD > gpurun_out/ncu_gn.log 2>&1
+echo "gn_apply capture rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:fir_up_kernel -c 2 -o gpurun_out/prof_fir_up $CMD > gpurun_out/ncu_fir.log 2>&1
+echo "fir capture rc=$?"
+ls -la gpurun_out/ | head -30
