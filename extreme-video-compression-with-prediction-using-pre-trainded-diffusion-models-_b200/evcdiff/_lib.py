@@ -31,6 +31,12 @@ class GemmDesc(C.Structure):
                 ("alpha", C.c_float), ("max_ctas", C.c_int32), ("stats", C.c_void_p), ("stride", C.c_int32), ("cta_group", C.c_int32)]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [("qk", C.c_void_p), ("qk_ld", C.c_int64), ("vT", C.c_void_p), ("vT_ld", C.c_int64),
+                ("out", C.c_void_p), ("out_ld", C.c_int64), ("B", C.c_int32), ("N", C.c_int32), ("C", C.c_int32),
+                ("heads", C.c_int32), ("scale", C.c_float)]
+
+
 class StepCoef(C.Structure):
     _fields_ = [("mode", C.c_int32), ("clip", C.c_int32), ("k0", C.c_float), ("k1", C.c_float),
                 ("c_x0", C.c_float), ("c_x", C.c_float), ("c_eps", C.c_float), ("c_noise", C.c_float)]
@@ -52,6 +58,10 @@ SIGNATURES = {
     "evc_gemm_plan_destroy": (None, [_vp]),
     "evc_gemm_plan_flops": (C.c_double, [_vp]),
     "evc_gemm_plan_cta_group": (C.c_int, [_vp]),
+    "evc_attn_plan_create": (C.c_int, [C.POINTER(AttnDesc), C.POINTER(C.c_void_p)]),
+    "evc_attn_plan_launch": (C.c_int, [_vp, _vp]),
+    "evc_attn_plan_destroy": (None, [_vp]),
+    "evc_attn_plan_flops": (C.c_double, [_vp]),
     "evc_gn_stats_workspace": (C.c_int, [_i32, _i32, _i32, C.POINTER(C.c_int64)]),
     "evc_gn_stats": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
     "evc_gn_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _vp, _i32, _i32, _vp, _vp]),

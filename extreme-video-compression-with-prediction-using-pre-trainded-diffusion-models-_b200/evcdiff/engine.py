@@ -13,6 +13,7 @@ Layout decisions (DESIGN.md has the full table):
   AdaGN         scale/shift rows of a per-label table evaluated before the loop (labels are batch-uniform)
 """
 import math
+import os
 
 import torch
 
@@ -88,6 +89,7 @@ class EngineBase:
         self._stat_acts = []
         self._deferred = []
         self.fixed_groups = None  # models/unet.py: always 32 groups; NCSN++: min(C//4, 32)
+        self.fused_attention = os.environ.get("EVC_FUSED_ATTENTION", "1") != "0"
         self.ws_bytes = 256
 
     # ----------------------------------------------------------------- recording helpers
@@ -192,8 +194,9 @@ class EngineBase:
 
     def attn_core(self, x, ss, gn_eps, ws, bs, heads, out_alpha):
         """out = out_alpha * (x + OUT(softmax(q k^T / sqrt(d)) v)) with q,k,v = 1x1 projections of GN(x).
-        ws/bs: [Wq, Wk, Wv, Wo] as (out, in) bf16 and fp32 biases.  Unfused round-1 attention: batched GEMMs with a
-        per-sample B operand (K, then V^T written by a transposed-store epilogue) + row softmax."""
+        ws/bs: [Wq, Wk, Wv, Wo] as (out, in) bf16 and fp32 biases.  The softmax(QK^T)V core is the fused tcgen05
+        attention kernel (evc_attn_*) when N % 128 == 0 and the head dim is a multiple of 64 (<= 384); otherwise
+        batched GEMMs with a per-sample B operand (K, then V^T from a transposed-store epilogue) + row softmax."""
         dev = self.device
         C, N, B = x.C, x.H * x.W, self.B
         d = C // heads
@@ -210,7 +213,11 @@ class EngineBase:
         # key axis padded to a multiple of 8 (16-byte TMA strides); only toy shapes (N < 8) ever pad.  Pad columns:
         # S = -inf (never written by the GEMM, so softmax gives P = 0) and V^T = 0.
         Np = max(8, (N + 7) // 8 * 8)
-        if Np == N:
+        fused = self.fused_attention and ops.attn_supported(N, C, heads)
+        S = Pm = None
+        if fused:
+            vT = self.pool.get((B, C, N))
+        elif Np == N:
             vT = self.pool.get((B, C, N))
             S = self.pool.get((B, N, N), torch.float32)
             Pm = self.pool.get((B, N, N))
@@ -222,17 +229,25 @@ class EngineBase:
         o = self.new_act(x.H, x.W, C)
         qk3 = qk.view(B, N, 2 * C)
         o3 = o.t.view(B, N, C)
-        for hd in range(heads):
-            q = qk3[:, :, hd * d:(hd + 1) * d].unsqueeze(1)  # (B,1,N,d)
-            k = qk3[:, :, C + hd * d:C + (hd + 1) * d]  # (B,N,d)  per-sample B operand
-            self.gemm([(q, 1)], k, S, EVC_OUT_F32_ROWS, Np, alpha=float(int(d) ** (-0.5)))
-            self._op(lambda li, S=S, Pm=Pm: ops.softmax_rows(S, Pm, B * N, Np), "softmax",
-                     dict(bytes=B * N * Np * 6))
-            self.gemm([(Pm.view(B, 1, N, Np), 1)], vT[:, hd * d:(hd + 1) * d, :], o3[:, :, hd * d:], EVC_OUT_BF16_ROWS, C)
+        if fused:
+            plan = ops.AttnPlan(qk3, vT, o3, heads, float(int(d) ** (-0.5)))
+            self.flops += plan.flops
+            self._op(lambda li, plan=plan: plan.launch(), "attn", dict(flops=plan.flops, N=N, d=d, heads=heads))
+        else:
+            for hd in range(heads):
+                q = qk3[:, :, hd * d:(hd + 1) * d].unsqueeze(1)  # (B,1,N,d)
+                k = qk3[:, :, C + hd * d:C + (hd + 1) * d]  # (B,N,d)  per-sample B operand
+                self.gemm([(q, 1)], k, S, EVC_OUT_F32_ROWS, Np, alpha=float(int(d) ** (-0.5)))
+                self._op(lambda li, S=S, Pm=Pm: ops.softmax_rows(S, Pm, B * N, Np), "softmax",
+                         dict(bytes=B * N * Np * 6))
+                self.gemm([(Pm.view(B, 1, N, Np), 1)], vT[:, hd * d:(hd + 1) * d, :], o3[:, :, hd * d:],
+                          EVC_OUT_BF16_ROWS, C)
         out = self.new_act(x.H, x.W, C, scratch=False)
         self.gemm([(o, 1)], wo, out.t, EVC_OUT_BF16_ROWS, C, bias=bo, resid=x, alpha=out_alpha, stats_of=out)
         self.pool.put(qk)
-        if Np == N:
+        if fused:
+            self.pool.put(vT)
+        elif Np == N:
             self.pool.put(vT); self.pool.put(S); self.pool.put(Pm)
         else:
             self._keep += [vT, S, Pm]

@@ -5,8 +5,8 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (EVC_OUT_BF16_ROWS, EVC_OUT_BF16_T, EVC_OUT_F32_ROWS, EVC_OUT_F32_T, GemmDesc, PndmCoef, StepCoef,
-                   check, load, stream_ptr)
+from ._lib import (EVC_OUT_BF16_ROWS, EVC_OUT_BF16_T, EVC_OUT_F32_ROWS, EVC_OUT_F32_T, AttnDesc, GemmDesc, PndmCoef,
+                   StepCoef, check, load, stream_ptr)
 
 
 def _ptr(t):
@@ -93,6 +93,44 @@ class GemmPlan:
         try:
             if getattr(self, "_h", None):
                 self._lib.evc_gemm_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def attn_supported(N, C, heads):
+    d = C // heads
+    return N % 128 == 0 and d % 64 == 0 and d <= 384 and (d <= 256 or d % 128 == 0)
+
+
+class AttnPlan:
+    """Fused attention launch: out (B,N,C) = softmax(scale q k^T) v per head, from qk (B,N,2C) and vT (B,C,N)."""
+
+    def __init__(self, qk, vT, out, heads, scale):
+        lib = load()
+        _require_cuda(qk, vT, out)
+        B, N, C2 = qk.shape
+        Cc = C2 // 2
+        assert vT.shape == (B, Cc, N) and out.shape[:2] == (B, N) and qk.stride(2) == 1 and vT.stride(2) == 1
+        d = AttnDesc()
+        d.qk, d.qk_ld = qk.data_ptr(), qk.stride(1)
+        d.vT, d.vT_ld = vT.data_ptr(), vT.stride(1)
+        d.out, d.out_ld = out.data_ptr(), out.stride(1)
+        d.B, d.N, d.C, d.heads, d.scale = B, N, Cc, heads, scale
+        self._keep = (qk, vT, out)
+        self._lib = lib
+        h = C.c_void_p()
+        check(lib.evc_attn_plan_create(C.byref(d), C.byref(h)), "evc_attn_plan_create")
+        self._h = h
+        self.flops = lib.evc_attn_plan_flops(h)
+
+    def launch(self):
+        check(self._lib.evc_attn_plan_launch(self._h, stream_ptr()), "evc_attn_plan_launch")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.evc_attn_plan_destroy(self._h)
                 self._h = None
         except Exception:
             pass

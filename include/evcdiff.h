@@ -113,6 +113,30 @@ double evc_gemm_plan_flops(const evc_gemm_plan* plan);
 int evc_gemm_plan_cta_group(const evc_gemm_plan* plan);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused self-attention forward (flash-style, tcgen05): out[b, q, h*d + :] = softmax(scale * Q_h K_h^T) V_h with
+ *   Q_h = qk[b, q, h*d : (h+1)*d],  K_h = qk[b, k, C + h*d : C + (h+1)*d]   (qk: (B, N, >= 2C) bf16 rows, row stride qk_ld)
+ *   V_h^T = vT[b, h*d : (h+1)*d, k]                                          (vT: (B, C, N) bf16, row stride vT_ld)
+ * Replaces einsum -> softmax -> einsum of AttnBlockpp / AttnBlock (layerspp.py:239-243, unet.py:114-119); the N x N
+ * score matrix never leaves the SM.  Needs N % 128 == 0, d = C/heads % 64 == 0, d <= 384 (EVC_ERR_UNSUPPORTED
+ * otherwise: the caller then uses the batched-GEMM + evc_softmax_rows formulation).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct evc_attn_desc {
+  const void* qk;
+  int64_t qk_ld;
+  const void* vT;
+  int64_t vT_ld;
+  void* out;       /* (B, N, out_ld >= C) bf16 rows */
+  int64_t out_ld;
+  int32_t B, N, C, heads;
+  float scale;
+} evc_attn_desc;
+typedef struct evc_attn_plan evc_attn_plan;
+int evc_attn_plan_create(const evc_attn_desc* desc, evc_attn_plan** plan);
+int evc_attn_plan_launch(const evc_attn_plan* plan, evc_stream_t stream);
+void evc_attn_plan_destroy(evc_attn_plan* plan);
+double evc_attn_plan_flops(const evc_attn_plan* plan);
+
+/* ------------------------------------------------------------------------------------------------
  * GroupNorm statistics and the fused normalise / AdaGN / affine / SiLU pass.
  * Replaces nn.GroupNorm + get_act_norm (layerspp.py:465-549) and Normalize+Swish (unet.py:44-46,90-95).
  * ---------------------------------------------------------------------------------------------- */
