@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
   const int d = p.d, kc_n = d / 64;
-  const int T = p.N / kBK;  // key tiles
+  const int T = p.N / kBK;  // key tiles (N % 64 == 0; a 64-query sample uses half of the 128-row tile, TMA zero-fills the rest)
   // shared memory: Q [kc_n][128x64] | ring [stages][64*d*2 B] | P [2][128x64] | barriers
   const uint32_t q_bytes = kBQ * d * 2u;
   const uint32_t st_bytes = kBK * d * 2u;
@@ -233,10 +233,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_
     tc_fence_after();
     const float inv = 1.f / l;
     __nv_bfloat16* orow = p.out + ((long long)b * p.N + q0 + row) * p.out_ld + head * d;
+    const bool row_valid = (q0 + row) < p.N;
     for (int c0 = 0; c0 < d; c0 += 32) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_O + lane_off + c0, v);
       tmem_ld_wait();
+      if (!row_valid) continue;
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         uint4 u;
@@ -288,8 +290,8 @@ extern "C" int evc_attn_plan_create(const evc_attn_desc* a, evc_attn_plan** out)
   if (!a->qk || !a->vT || !a->out || a->B < 1 || a->heads < 1 || a->C < 64 || (a->C % a->heads))
     return evc_set_error(EVC_ERR_INVALID, "evc_attn_plan_create: bad arguments");
   const int d = a->C / a->heads;
-  if ((a->N % kBQ) != 0 || (d % 64) != 0 || d > 384 || (d > 256 && (d % 128) != 0))
-    return evc_set_error(EVC_ERR_UNSUPPORTED, "fused attention needs N % 128 == 0, head dim % 64 == 0, head dim <= 384");
+  if ((a->N % kBK) != 0 || (d % 64) != 0 || d > 384 || (d > 256 && (d % 128) != 0))
+    return evc_set_error(EVC_ERR_UNSUPPORTED, "fused attention needs N % 64 == 0, head dim % 64 == 0, head dim <= 384");
   if ((a->qk_ld % 8) || (a->vT_ld % 8) || (a->out_ld % 8) || (reinterpret_cast<uintptr_t>(a->qk) & 15) ||
       (reinterpret_cast<uintptr_t>(a->vT) & 15) || (reinterpret_cast<uintptr_t>(a->out) & 15))
     return evc_set_error(EVC_ERR_INVALID, "evc_attn_plan_create: 16-byte alignment required");
@@ -320,7 +322,7 @@ extern "C" int evc_attn_plan_create(const evc_attn_desc* a, evc_attn_plan** out)
   }
   p.num_stages = stages;
   pl->smem_bytes = 1024 + q_bytes + stages * st_bytes + p_bytes + 512;
-  pl->grid = dim3(a->N / kBQ, a->heads, a->B);
+  pl->grid = dim3((a->N + kBQ - 1) / kBQ, a->heads, a->B);
   pl->flops = 4.0 * a->B * (double)a->N * a->N * a->C;  // QK^T + PV (the recomputed QK^T is not counted)
   *out = pl;
   return EVC_OK;

@@ -195,7 +195,7 @@ class EngineBase:
     def attn_core(self, x, ss, gn_eps, ws, bs, heads, out_alpha):
         """out = out_alpha * (x + OUT(softmax(q k^T / sqrt(d)) v)) with q,k,v = 1x1 projections of GN(x).
         ws/bs: [Wq, Wk, Wv, Wo] as (out, in) bf16 and fp32 biases.  The softmax(QK^T)V core is the fused tcgen05
-        attention kernel (evc_attn_*) when N % 128 == 0 and the head dim is a multiple of 64 (<= 384); otherwise
+        attention kernel (evc_attn_*) when N % 64 == 0 and the head dim is a multiple of 64 (<= 384); otherwise
         batched GEMMs with a per-sample B operand (K, then V^T from a transposed-store epilogue) + row softmax."""
         dev = self.device
         C, N, B = x.C, x.H * x.W, self.B

@@ -100,7 +100,7 @@ class GemmPlan:
 
 def attn_supported(N, C, heads):
     d = C // heads
-    return N % 128 == 0 and d % 64 == 0 and d <= 384 and (d <= 256 or d % 128 == 0)
+    return N % 64 == 0 and d % 64 == 0 and d <= 384 and (d <= 256 or d % 128 == 0)
 
 
 class AttnPlan:

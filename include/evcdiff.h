@@ -117,7 +117,7 @@ int evc_gemm_plan_cta_group(const evc_gemm_plan* plan);
  *   Q_h = qk[b, q, h*d : (h+1)*d],  K_h = qk[b, k, C + h*d : C + (h+1)*d]   (qk: (B, N, >= 2C) bf16 rows, row stride qk_ld)
  *   V_h^T = vT[b, h*d : (h+1)*d, k]                                          (vT: (B, C, N) bf16, row stride vT_ld)
  * Replaces einsum -> softmax -> einsum of AttnBlockpp / AttnBlock (layerspp.py:239-243, unet.py:114-119); the N x N
- * score matrix never leaves the SM.  Needs N % 128 == 0, d = C/heads % 64 == 0, d <= 384 (EVC_ERR_UNSUPPORTED
+ * score matrix never leaves the SM.  Needs N % 64 == 0, d = C/heads % 64 == 0, d <= 384 (EVC_ERR_UNSUPPORTED
  * otherwise: the caller then uses the batched-GEMM + evc_softmax_rows formulation).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct evc_attn_desc {

@@ -10,7 +10,7 @@ def rel_l2(a, b):
 
 
 @pytest.mark.parametrize("B,N,C,heads", [(2, 1024, 384, 2), (3, 256, 576, 3), (1, 128, 64, 1), (2, 256, 256, 1),
-                                          (1, 4096, 384, 1), (2, 128, 768, 4), (5, 1024, 128, 2)])
+                                          (1, 4096, 384, 1), (2, 128, 768, 4), (5, 1024, 128, 2), (5, 64, 768, 4), (3, 192, 128, 2)])
 def test_fused_attention(B, N, C, heads):
     torch.backends.cuda.matmul.allow_tf32 = False
     from evcdiff import ops
