@@ -165,6 +165,8 @@ class NCSNpp(nn.Module):
         device = torch.device(device) if device is not None else next(self.parameters()).device
         if device.type != "cuda":
             raise EvcError("evcdiff runs on CUDA devices only; move the model with .to('cuda')")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         key = (B, str(device))
         ver = self._weights_version()
         hit = self._engines.get(key)

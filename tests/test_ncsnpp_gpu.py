@@ -223,3 +223,44 @@ def test_ddpm100_trajectory():
     fr = lambda z: torch.clamp((z + 1) / 2, 0, 1)
     p_ours, p_ref = common.psnr(fr(imgs[-1].to(DEV)), target), common.psnr(fr(trace[-1][0]), target)
     assert abs(p_ours - p_ref) < 0.05, (p_ours, p_ref)
+
+
+def test_ddim_step_sweep_and_pndm_api():
+    """BASELINE config 4 (DDIM 10/25/50/100/1000 -> 11/26/51/101/1001 evaluations, one graph per schedule) on the
+    gpu64 network at default-like init, and the public pndm functions driven eagerly (reference models/pndm.py)."""
+    from evcdiff import models as M
+    from evcdiff import ops
+    from evcdiff.models import pndm
+    cfg, net, sd = build(common.gpu64_config, 4, active=False)
+    g = torch.Generator(device=DEV).manual_seed(33)
+    x_T = torch.randn(1, 15, 32, 32, device=DEV, generator=g)
+    cond = torch.rand(1, 6, 32, 32, device=DEV, generator=g, dtype=torch.float64) * 2 - 1
+    model = lambda xx, yy: net(xx, yy, cond=cond)
+    sched = (net.betas, net.alphas, net.alphas_prev)
+    per_eval = None
+    for steps in (10, 25, 50, 100, 1000):
+        n0 = ops.launch_count()
+        y = M.ddim_sampler(x_T.clone(), net, cond=cond, final_only=True, denoise=True, subsample_steps=steps)
+        assert y.shape == (1, 1, 15, 32, 32) and torch.isfinite(y).all()
+        loop = net.engine(1, DEV)._loop
+        launched = max(v for k, v in loop.launches_per_run.items() if k[0] == "ddim" and k[1] == min(steps, 1000))
+        evals = steps + 1
+        if per_eval is None:
+            per_eval = (launched - evals) / evals  # UNet launches + 1 update per evaluation
+        assert launched == round(evals * (per_eval + 1)), (steps, launched)
+        if steps <= 50:
+            ref = S.ddim_sampler(x_T.clone(), model, sched, subsample_steps=steps)
+            assert common.rel_l2(y[0], ref) < 2e-3, (steps, common.rel_l2(y[0], ref))
+    # pndm API (eager): gen_order_4 for 4 steps = 3 Runge-Kutta steps + 1 Adams-Bashforth step, and gen_order_1
+    a_old = net.alphas.flip(0)
+    x1, x2, ets1, ets2 = x_T.clone(), x_T.clone(), [], []
+    for t, tn in [(0, -1), (100, 0), (200, 100), (300, 200)]:
+        tt = torch.full((1,), t, device=DEV).long()
+        tnn = torch.full((1,), tn, device=DEV).long()
+        x1, ets1 = pndm.gen_order_4(x1, tt, tnn, model, a_old, ets1, clip_before=True)
+        x2, ets2 = S.gen_order_4(x2, tt, tnn, model, a_old, ets2, clip_before=True)
+    assert len(ets1) == 4 and common.rel_l2(x1, x2) < 2e-3
+    tt, tnn = torch.full((1,), 500, device=DEV).long(), torch.full((1,), 400, device=DEV).long()
+    y1, _ = pndm.gen_order_1(x_T, tt, tnn, model, a_old, [], clip_before=False)
+    y2, _ = S.gen_order_1(x_T, tt, tnn, model, a_old, [], clip_before=False)
+    assert common.rel_l2(y1, y2) < 1e-5
