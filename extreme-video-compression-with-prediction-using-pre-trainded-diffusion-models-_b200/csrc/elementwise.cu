@@ -199,14 +199,23 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
   __nv_bfloat16* dst = y + ((long long)b * HW + p0) * C + c;
   const long long sstep = (long long)rows * ld, dstep = (long long)rows * C;
   int n = (p0 < p_end) ? (p_end - p0 + rows - 1) / rows : 0;  // pixels this thread handles
-  for (; n >= 4; n -= 4) {
-    uint4 u[4];
+  // software pipeline: the loads of the next four pixels are in flight while the current four are normalised
+  uint4 cur[4];
+  if (n >= 4) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = ld_nc16(src + k * sstep);
+    for (int k = 0; k < 4; ++k) cur[k] = ld_nc16(src + k * sstep);
+  }
+  while (n >= 4) {
+    uint4 nxt[4];
+    const bool more = (n >= 8);
+    if (more) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) nxt[k] = ld_nc16(src + (4 + k) * sstep);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float f[8];
-      unpack8(u[k], f);
+      unpack8(cur[k], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float t = fmaf(f[j], a[j], bb[j]);
@@ -216,6 +225,11 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
     }
     src += 4 * sstep;
     dst += 4 * dstep;
+    n -= 4;
+    if (more) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
+    }
   }
   for (; n > 0; --n) {
     float f[8];

@@ -120,6 +120,42 @@ __global__ void linear_f32_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
+// Per-frame PSNR in float64 like city_sender.cal_psnr (:255-258): one block per frame, fixed-order tree reduction.
+__global__ void frame_psnr_kernel(const float* __restrict__ a, const float* __restrict__ b, long long frame_elems,
+                                  double maxvalue, double* __restrict__ psnr) {
+  __shared__ double sred[256];
+  const long long f = blockIdx.x;
+  const float* pa = a + f * frame_elems;
+  const float* pb = b + f * frame_elems;
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < frame_elems; i += blockDim.x) {
+    const double d = (double)pa[i] - (double)pb[i];
+    acc += d * d;
+  }
+  sred[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sred[threadIdx.x] += sred[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) psnr[f] = 10.0 * log10((maxvalue * maxvalue) / (sred[0] / (double)frame_elems));
+}
+
+// counts[v] = length of the longest prefix of video v's F frames whose score passes the threshold
+// (decide_5to5, city_sender.py:353-374: accept frames until the first failure).
+__global__ void accept_prefix_kernel(const double* __restrict__ score, int V, int F, double threshold, int higher_is_better,
+                                     int* __restrict__ counts) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  int n = 0;
+  for (; n < F; ++n) {
+    const double s = score[(long long)v * F + n];
+    const bool ok = higher_is_better ? (s >= threshold) : (s <= threshold);
+    if (!ok) break;
+  }
+  counts[v] = n;
+}
+
 }  // namespace evc
 
 using namespace evc;
@@ -175,4 +211,19 @@ extern "C" int evc_linear_f32(const float* x, const float* W, const float* b, fl
   dim3 grid((N + warps - 1) / warps, (L + kLinTile - 1) / kLinTile);
   linear_f32_kernel<<<grid, warps * 32, 0, (cudaStream_t)stream>>>(x, W, b, y, L, K, N, act_in, act_out);
   return evc_check_launch("linear_f32_kernel");
+}
+
+extern "C" int evc_frame_psnr(const float* a, const float* b, int32_t n_frames, int64_t frame_elems, double maxvalue,
+                              double* psnr, evc_stream_t stream) {
+  if (!a || !b || !psnr || n_frames < 1 || frame_elems < 1) return evc_set_error(EVC_ERR_INVALID, "evc_frame_psnr: bad arguments");
+  frame_psnr_kernel<<<n_frames, 256, 0, (cudaStream_t)stream>>>(a, b, frame_elems, maxvalue, psnr);
+  return evc_check_launch("frame_psnr_kernel");
+}
+
+extern "C" int evc_accept_prefix(const double* score, int32_t n_videos, int32_t n_frames, double threshold,
+                                 int32_t higher_is_better, int32_t* counts, evc_stream_t stream) {
+  if (!score || !counts || n_videos < 1 || n_frames < 1) return evc_set_error(EVC_ERR_INVALID, "evc_accept_prefix: bad arguments");
+  accept_prefix_kernel<<<(n_videos + 127) / 128, 128, 0, (cudaStream_t)stream>>>(score, n_videos, n_frames, threshold,
+                                                                                higher_is_better, counts);
+  return evc_check_launch("accept_prefix_kernel");
 }

@@ -76,6 +76,8 @@ SIGNATURES = {
     "evc_pndm_update": (C.c_int, [_vp, C.POINTER(C.c_void_p), _vp, _vp, _vp, _i32, _i32, _i32, _i32,
                                   C.POINTER(PndmCoef), _vp]),
     "evc_inverse_transform": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "evc_frame_psnr": (C.c_int, [_vp, _vp, _i32, _i64, C.c_double, _vp, _vp]),
+    "evc_accept_prefix": (C.c_int, [_vp, _i32, _i32, C.c_double, _i32, _vp, _vp]),
 }
 
 _lib = None

@@ -264,5 +264,28 @@ def inverse_transform(x, frames):
     check(load().evc_inverse_transform(_ptr(x), _ptr(frames), x.numel(), stream_ptr()), "evc_inverse_transform")
 
 
+def frame_psnr(a, b, maxvalue=1.0):
+    """a, b: (..., C, H, W) fp32 with identical shapes, leading dims = frames.  Returns float64 PSNR per frame."""
+    _require_cuda(a, b)
+    assert a.shape == b.shape and a.dtype == torch.float32 and b.dtype == torch.float32
+    a, b = a.contiguous(), b.contiguous()
+    frame_elems = a.shape[-1] * a.shape[-2] * a.shape[-3]
+    n = a.numel() // frame_elems
+    out = torch.empty(a.shape[:-3], dtype=torch.float64, device=a.device)
+    check(load().evc_frame_psnr(_ptr(a), _ptr(b), n, frame_elems, float(maxvalue), _ptr(out), stream_ptr()),
+          "evc_frame_psnr")
+    return out
+
+
+def accept_prefix(score, threshold, higher_is_better=True):
+    """score (V, F) float64 -> int32 (V,): frames accepted before the first one failing the threshold."""
+    _require_cuda(score)
+    V, F = score.shape
+    counts = torch.empty((V,), dtype=torch.int32, device=score.device)
+    check(load().evc_accept_prefix(_ptr(score.contiguous()), V, F, float(threshold), int(higher_is_better), _ptr(counts),
+                                   stream_ptr()), "evc_accept_prefix")
+    return counts
+
+
 def launch_count():
     return int(load().evc_launch_count())

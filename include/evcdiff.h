@@ -219,6 +219,17 @@ int evc_pndm_update(const float* x, const float* const* e_host, float* x_out, fl
 /* frames = clamp((x+1)/2, 0, 1), NCHW fp32 -> NCHW fp32 (inverse_data_transform, function.py:73-82) */
 int evc_inverse_transform(const float* x, float* frames, int64_t n, evc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Sender-side accept decision on the GPU (next rows of the path): per-frame PSNR in float64
+ * (city_sender.py:255-258 cal_psnr) and the accept-until-first-failure prefix of decide_5to5 (:353-374).
+ * ---------------------------------------------------------------------------------------------- */
+/* psnr[f] = 10 log10(maxvalue^2 / mean((a_f - b_f)^2)), frames of frame_elems fp32 values */
+int evc_frame_psnr(const float* a, const float* b, int32_t n_frames, int64_t frame_elems, double maxvalue, double* psnr,
+                   evc_stream_t stream);
+/* counts[v] = number of leading frames of video v (n_frames scores each) passing the threshold */
+int evc_accept_prefix(const double* score, int32_t n_videos, int32_t n_frames, double threshold,
+                      int32_t higher_is_better, int32_t* counts, evc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

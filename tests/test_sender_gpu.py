@@ -1,0 +1,57 @@
+"""GPU tests of the batched sender loop: float64 PSNR, accept-prefix decision, autoregressive cycles."""
+import numpy as np
+import pytest
+import torch
+
+import common
+from oracle import ncsnpp as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cal_psnr(img1, img2, maxvalue=1.0):  # restatement of city_sender.py:255-258
+    img1, img2 = img1.astype(np.float64), img2.astype(np.float64)
+    mse = np.mean((img1 - img2) ** 2)
+    return 10 * np.log10((maxvalue ** 2) / mse)
+
+
+def test_psnr_and_accept_prefix():
+    from evcdiff import ops
+    g = torch.Generator(device=DEV).manual_seed(1)
+    a = torch.rand(4, 5, 3, 32, 32, device=DEV, generator=g)
+    b = (a + 0.05 * torch.randn(4, 5, 3, 32, 32, device=DEV, generator=g)).clamp(0, 1)
+    p = ops.frame_psnr(a, b)
+    ref = np.array([[cal_psnr(a[v, f].cpu().numpy(), b[v, f].cpu().numpy()) for f in range(5)] for v in range(4)])
+    assert p.dtype == torch.float64 and np.allclose(p.cpu().numpy(), ref, rtol=1e-12, atol=1e-10)
+    score = torch.tensor([[30, 31, 10, 40, 40], [5, 40, 40, 40, 40], [30, 30, 30, 30, 30], [30, 30, 30, 30, 29.9]],
+                         dtype=torch.float64, device=DEV)
+    assert ops.accept_prefix(score, 30.0).tolist() == [2, 0, 5, 4]
+    assert ops.accept_prefix(-score, -30.0, higher_is_better=False).tolist() == [2, 0, 5, 4]
+
+
+def test_batched_sender_cycles():
+    from evcdiff.models.better.ncsnpp_more import UNetMore_DDPM
+    from evcdiff.sender import BatchedSender
+    cfg = common.gpu64_config(device=DEV)
+    cfg.sampling.subsample = 5
+    net = UNetMore_DDPM(cfg)
+    net.load_state_dict(common.seeded_state_dict(O.ncsnpp_param_shapes(cfg), seed=4, active=True), strict=False)
+    net = net.to(DEV).eval()
+    g = torch.Generator(device=DEV).manual_seed(2)
+    V, T = 3, 12
+    x_gt = torch.rand(V, T, 3, 32, 32, device=DEV, generator=g)
+    # threshold -inf: every predicted frame is accepted -> 2 keyframes then 5 frames per cycle
+    x_ge, d, n = BatchedSender(net, cfg, threshold=-1e30).encode(x_gt)
+    assert n == 2 and x_ge.shape == x_gt.shape
+    assert d.tolist() == [[1, 1] + [0] * 10] * V
+    assert torch.equal(x_ge[:, :2], x_gt[:, :2]) and float(x_ge.min()) >= 0.0 and float(x_ge.max()) <= 1.0
+    # threshold +inf: nothing is ever accepted -> every frame is a keyframe, two per cycle
+    x_ge, d, n = BatchedSender(net, cfg, threshold=1e30).encode(x_gt)
+    assert n == 5 and torch.equal(x_ge, x_gt) and int(d.min()) == 1
+    # mixed: accept only frames with PSNR above the median PSNR of a probe cycle; invariants of the flag array
+    sender = BatchedSender(net, cfg, threshold=7.0)
+    x_ge, d, n = sender.encode(x_gt)
+    assert x_ge.shape == x_gt.shape and set(d.unique().tolist()) <= {0, 1}
+    key = d.bool()
+    assert torch.equal(x_ge[key], x_gt[key])  # keyframes are the (lossless stand-in) ground truth

@@ -5,7 +5,8 @@ mkdir -p gpurun_out
 VAR=${1:-EVC_GEMM_CTA_GROUP}; A=${2:-1}; B=${3:-2}
 for rep in 1 2; do
   for v in $A $B; do
-    env $VAR=$v python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ab_${v}_$rep.json 2> gpurun_out/ab_${v}_$rep.err
+    env $VAR=$v python bench.py --steps 1 --warmup 1 --no-cpu-baseline --profile-json gpurun_out/ab_prof_${v}.json > gpurun_out/ab_${v}_$rep.json 2> gpurun_out/ab_${v}_$rep.err
+    tail -2 gpurun_out/ab_${v}_$rep.err
     python - <<PY
 import json
 d=json.load(open('gpurun_out/ab_${v}_$rep.json'))
