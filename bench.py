@@ -27,7 +27,10 @@ for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
 
 import torch  # noqa: E402
 
-GFLOP_PER_EVAL = 345.20  # dense GFLOP per sample per NCSN++ evaluation
+# dense GFLOP per sample per UNet evaluation
+GFLOP = {"ncsnpp": 345.20, "unet_deep": 566.17, "unet_deeper": 615.09}
+MODEL_NAME = {"ncsnpp": "configs/mine.yml NCSN++ (262.1 M parameters)", "unet_deep": "models/unet.py 'deep' (80.4 M parameters)",
+              "unet_deeper": "models/unet.py 'deeper' (240.9 M parameters)"}
 EVALS = {"ddpm": lambda s: s + 1, "ddim": lambda s: s + 1, "fpndm": lambda s: 12 + (s - 3)}
 
 
@@ -158,9 +161,10 @@ def run_reference(args):
 
 def workload_config(args, world):
     return {"workload": f"BASELINE.json configs[1]: city_bonn-shaped synthetic set, {args.videos} videos per GPU, "
-                        f"{args.sampler.upper()}-{args.subsample} ({EVALS[args.sampler](args.subsample)} NCSN++ evaluations per "
-                        f"cycle), configs/mine.yml model (262.1 M parameters, random init), 5 predicted 128x128 frames per "
+                        f"{args.sampler.upper()}-{args.subsample} ({EVALS[args.sampler](args.subsample)} UNet evaluations per "
+                        f"cycle), {MODEL_NAME[args.model]}, random init, 5 predicted 128x128 frames per "
                         f"video per step",
+            "model": args.model,
             "videos_per_gpu": args.videos, "sampler": args.sampler, "subsample": args.subsample,
             "micro_batch": args.micro_batch, "parallelism": f"shard-by-video x{world}, one NCCL gather per step",
             "l2": "working set (>= 2 GB of activations per evaluation) exceeds the 126 MB L2; no explicit flush"}
@@ -176,6 +180,8 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=46)
     ap.add_argument("--sampler", default="ddpm", choices=["ddpm", "ddim", "fpndm"])
     ap.add_argument("--subsample", type=int, default=100)
+    ap.add_argument("--model", default="ncsnpp", choices=["ncsnpp", "unet_deep", "unet_deeper"],
+                    help="ncsnpp = BASELINE configs[1-4]; unet_* = configs[4] (models/unet.py variant)")
     ap.add_argument("--ref-evals", type=int, default=4)
     ap.add_argument("--cpu-evals", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -204,10 +210,17 @@ def main():
     cfg = common.full_config(device=dev)
     cfg.sampling.subsample = args.subsample
     torch.manual_seed(0)
-    net = UNetMore_DDPM(cfg).to(dev).eval()
+    if args.model == "ncsnpp":
+        net = UNetMore_DDPM(cfg).to(dev).eval()
+    else:
+        from evcdiff.models.unet import UNet_DDPM
+        cfg.mode = "deep" if args.model == "unet_deep" else "deeper"
+        net = UNet_DDPM(cfg).to(dev).eval()
 
     videos = synthetic_videos(args.videos, seed=rank)
     data = torch.from_numpy(videos[:, :2].reshape(args.videos, 6, 128, 128)).double() / 255.0  # city_sender.py:487
+    if args.model != "ncsnpp":
+        data = data.float()  # models/unet.py never casts its input (a float64 cond crashes the reference's first conv)
     host_in = data.pin_memory()
     host_out = torch.empty((args.videos, 5, 3, 128, 128), dtype=torch.float32).pin_memory()
     dev_in = host_in.to(dev)
@@ -270,7 +283,7 @@ def main():
     value = frames_per_step * args.steps / (ms / 1e3)
     e2e = frames_per_step * args.steps / (ms_e2e / 1e3)
     evals = EVALS[args.sampler](args.subsample)
-    tflop_per_frame = GFLOP_PER_EVAL * evals / 5.0 / 1e3
+    tflop_per_frame = GFLOP[args.model] * evals / 5.0 / 1e3
 
     # ---- roofline of the dominant kernel (evc_gemm_kernel): CUDA events around every launch of one evaluation
     prof = eng.profile(0, reps=3)

@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_
   const uint32_t tmem_S = tmem_base;         // 2 x 64 columns
   const uint32_t tmem_O = tmem_base + 128u;  // d columns
 
+  pdl_wait();
+  pdl_trigger();
   const int cq = head * d;          // channel offset of this head's q
   const int ck = p.C + head * d;    // ... and k inside the fused [q | k] rows
 
@@ -336,7 +338,8 @@ extern "C" int evc_attn_plan_launch(const evc_attn_plan* pl, evc_stream_t stream
     if (e != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
     attr_set = true;
   }
-  evc_attn_kernel<<<pl->grid, kAttnThreads, pl->smem_bytes, (cudaStream_t)stream>>>(pl->p);
+  cudaError_t e = evc_launch(evc_attn_kernel, pl->grid, dim3(kAttnThreads), pl->smem_bytes, (cudaStream_t)stream, 1, pl->p);
+  if (e != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
   return evc_check_launch("evc_attn_kernel");
 }
 

@@ -50,6 +50,8 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
                                 float* __restrict__ partials, unsigned* __restrict__ tickets) {
   extern __shared__ float sred[];  // [rows][nvec][16]
   __shared__ unsigned s_last;
+  pdl_wait();
+  pdl_trigger();
   const int nvec = blockDim.x;
   const int v = threadIdx.x;
   const int r = threadIdx.y;
@@ -145,6 +147,8 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
                                                        __nv_bfloat16* __restrict__ y, int pix_per_block) {
   __shared__ float s_mean[64], s_rstd[64];
   __shared__ float s_ps[64][9], s_pq[64][9];
+  pdl_wait();
+  pdl_trigger();
   const int C = C0 + C1;
   const int b = blockIdx.y;
   const int cpg = C / groups;
@@ -255,6 +259,8 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
 // 9 loads for 4 stores instead of 16).  Horizontal pass first: L = (x[i-1] + 3 x[i]) / 4, R = (3 x[i] + x[i+1]) / 4.
 __global__ void fir_up_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W,
                               int C) {
+  pdl_wait();
+  pdl_trigger();
   const int nvec = C / 8;
   const int OW = 2 * W;
   const long long total = (long long)B * H * W * nvec;
@@ -313,6 +319,8 @@ __global__ void fir_up_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
 
 __global__ void fir_down_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
                                 int W, int C) {
+  pdl_wait();
+  pdl_trigger();
   const int nvec = C / 8;
   const int OH = H / 2, OW = W / 2;
   const long long total = (long long)B * OH * OW * nvec;
@@ -474,8 +482,10 @@ extern "C" int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, i
   float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + tick_bytes);
   dim3 block(nvec, rows), grid(chunks, B);
   const size_t smem = (size_t)rows * nvec * 16 * sizeof(float);
-  gn_stats_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C,
-                                                               reinterpret_cast<long long*>(stats), c_total, c_off, ppb, partials, tickets);
+  cudaError_t le = evc_launch(gn_stats_kernel, grid, block, smem, (cudaStream_t)stream, 1,
+                              reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (int)HW, (int)C,
+                              reinterpret_cast<long long*>(stats), (int)c_total, (int)c_off, ppb, partials, tickets);
+  if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
   return evc_check_launch("gn_stats_kernel");
 }
 
@@ -498,16 +508,12 @@ extern "C" int evc_gn_apply(const void* x0, int32_t C0, const void* x1, int32_t 
   const int ppb = (HW + chunks - 1) / chunks;
   chunks = (HW + ppb - 1) / ppb;
   dim3 grid(chunks, B), block(nvec, rows);
-  if (silu)
-    gn_apply_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1, HW,
-        reinterpret_cast<const long long*>(stats0), reinterpret_cast<const long long*>(stats1), groups, eps, ss, adagn,
-        reinterpret_cast<__nv_bfloat16*>(y), ppb);
-  else
-    gn_apply_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x0), C0, reinterpret_cast<const __nv_bfloat16*>(x1), C1, HW,
-        reinterpret_cast<const long long*>(stats0), reinterpret_cast<const long long*>(stats1), groups, eps, ss, adagn,
-        reinterpret_cast<__nv_bfloat16*>(y), ppb);
+  cudaError_t le = evc_launch(silu ? gn_apply_kernel<true> : gn_apply_kernel<false>, grid, block, 0, (cudaStream_t)stream, 1,
+                              reinterpret_cast<const __nv_bfloat16*>(x0), (int)C0, reinterpret_cast<const __nv_bfloat16*>(x1),
+                              (int)C1, (int)HW, reinterpret_cast<const long long*>(stats0),
+                              reinterpret_cast<const long long*>(stats1), (int)groups, eps, ss, (int)adagn,
+                              reinterpret_cast<__nv_bfloat16*>(y), ppb);
+  if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
   return evc_check_launch("gn_apply_kernel");
 }
 
@@ -518,12 +524,10 @@ extern "C" int evc_fir_resample(const void* x, void* y, int32_t B, int32_t H, in
   const long long work = up ? (long long)B * H * W : (long long)B * (H / 2) * (W / 2);  // threads: input px (up) / output px
   const long long items = work * (C / 8);
   const int grid = grid_for(items, 256);
-  if (up)
-    fir_up_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                          reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
-  else
-    fir_down_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                            reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
+  cudaError_t le = evc_launch(up ? fir_up_kernel : fir_down_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 1,
+                              reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), (int)B, (int)H,
+                              (int)W, (int)C);
+  if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
   return evc_check_launch("fir_resample");
 }
 

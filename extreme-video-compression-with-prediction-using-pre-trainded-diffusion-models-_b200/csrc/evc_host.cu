@@ -1,4 +1,6 @@
 // Error state, driver entry points and device properties for libevcdiff.so.
+#include <stdlib.h>
+
 #include "evc_host.h"
 
 #include <atomic>
@@ -39,6 +41,23 @@ PFN_encodeTiled evc_get_encode_tiled() {
   });
   return fn;
 }
+
+// Programmatic dependent launch: -1 = not decided (use EVC_PDL or default off), 0 / 1 = set by evc_set_pdl.
+// Measured on B200 (profiles/r01_notes.md): +4 % at batch 1 (launch-latency bound), -0.5 % at batch 46.
+static std::atomic<int> g_pdl{-1};
+
+int evc_pdl_enabled() {
+  static int env = -2;
+  if (env == -2) {
+    const char* e = getenv("EVC_PDL");
+    env = (e == nullptr) ? -1 : (e[0] == '0' ? 0 : 1);
+  }
+  if (env >= 0) return env;  // the environment variable overrides everything (A/B runs)
+  const int v = g_pdl.load();
+  return v < 0 ? 0 : v;
+}
+
+extern "C" void evc_set_pdl(int enabled) { g_pdl.store(enabled ? 1 : 0); }
 
 int evc_num_sms() {
   static int sms = 0;

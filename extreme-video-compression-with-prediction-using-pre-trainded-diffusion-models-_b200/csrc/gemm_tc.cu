@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
 
   const int m_pairs = (p.m_tiles + CG - 1) / CG;
   const int total_tiles = m_pairs * p.tiles_n;
+  pdl_wait();     // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -638,29 +640,12 @@ extern "C" int evc_gemm_plan_launch(const evc_gemm_plan* pl, const float* bias_o
   }
   GemmParams p = pl->p;
   if (bias_override != nullptr) p.bias = bias_override;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(pl->grid);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = pl->smem_bytes;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
   cudaError_t e;
-  if (pl->cg == 2) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, evc_gemm_kernel<2>, p);
-  } else {
-    e = cudaLaunchKernelEx(&cfg, evc_gemm_kernel<1>, p);
-  }
-  if (e != cudaSuccess) {
-    (void)cudaGetLastError();
-    return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
-  }
+  if (pl->cg == 2)
+    e = evc_launch(evc_gemm_kernel<2>, dim3(pl->grid), dim3(kThreads), pl->smem_bytes, (cudaStream_t)stream, 2, p);
+  else
+    e = evc_launch(evc_gemm_kernel<1>, dim3(pl->grid), dim3(kThreads), pl->smem_bytes, (cudaStream_t)stream, 1, p);
+  if (e != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
   return evc_check_launch(pl->cg == 2 ? "evc_gemm_kernel<2>" : "evc_gemm_kernel<1>");
 }
 

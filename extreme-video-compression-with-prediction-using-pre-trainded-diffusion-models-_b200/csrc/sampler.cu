@@ -13,6 +13,8 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
                                       const float* __restrict__ noise, float* __restrict__ x_out,
                                       __nv_bfloat16* __restrict__ xin, int B, int C, int HW, int Cpad,
                                       evc_step_coef k) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)B * HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / HW);
@@ -48,6 +50,8 @@ struct PndmArgs {
 __global__ void pndm_update_kernel(const float* __restrict__ x, PndmArgs a, float* __restrict__ x_out,
                                    float* __restrict__ et_out, __nv_bfloat16* __restrict__ xin, int B, int C, int HW,
                                    int Cpad) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)B * HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / HW);
@@ -175,8 +179,10 @@ extern "C" int evc_sampler_update(const float* x, const float* eps, const float*
     return evc_set_error(EVC_ERR_INVALID, "evc_sampler_update: bad arguments");
   if (coef_host->mode == 0 && coef_host->c_noise != 0.f && noise == nullptr)
     return evc_set_error(EVC_ERR_INVALID, "evc_sampler_update: noise required");
-  sampler_update_kernel<<<grid_px((long long)B * HW), 256, 0, (cudaStream_t)stream>>>(
-      x, eps, noise, x_out, reinterpret_cast<__nv_bfloat16*>(xin), B, C, HW, Cpad, *coef_host);
+  cudaError_t le = evc_launch(sampler_update_kernel, dim3(grid_px((long long)B * HW)), dim3(256), 0, (cudaStream_t)stream, 1,
+                              x, eps, noise, x_out, reinterpret_cast<__nv_bfloat16*>(xin), (int)B, (int)C, (int)HW, (int)Cpad,
+                              *coef_host);
+  if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
   return evc_check_launch("sampler_update_kernel");
 }
 
@@ -191,8 +197,9 @@ extern "C" int evc_pndm_update(const float* x, const float* const* e_host, float
   for (int j = 0; j < coef_host->n_e; ++j)
     if (a.e[j] == nullptr) return evc_set_error(EVC_ERR_INVALID, "evc_pndm_update: null eps pointer");
   a.k = *coef_host;
-  pndm_update_kernel<<<grid_px((long long)B * HW), 256, 0, (cudaStream_t)stream>>>(
-      x, a, x_out, et_out, reinterpret_cast<__nv_bfloat16*>(xin), B, C, HW, Cpad);
+  cudaError_t le = evc_launch(pndm_update_kernel, dim3(grid_px((long long)B * HW)), dim3(256), 0, (cudaStream_t)stream, 1,
+                              x, a, x_out, et_out, reinterpret_cast<__nv_bfloat16*>(xin), (int)B, (int)C, (int)HW, (int)Cpad);
+  if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
   return evc_check_launch("pndm_update_kernel");
 }
 

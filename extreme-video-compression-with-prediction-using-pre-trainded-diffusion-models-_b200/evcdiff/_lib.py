@@ -53,6 +53,7 @@ SIGNATURES = {
     "evc_version": (C.c_int, []),
     "evc_last_error": (C.c_char_p, []),
     "evc_launch_count": (C.c_int64, []),
+    "evc_set_pdl": (None, [C.c_int]),
     "evc_gemm_plan_create": (C.c_int, [C.POINTER(GemmDesc), C.POINTER(C.c_void_p)]),
     "evc_gemm_plan_launch": (C.c_int, [_vp, _vp, _vp]),
     "evc_gemm_plan_destroy": (None, [_vp]),

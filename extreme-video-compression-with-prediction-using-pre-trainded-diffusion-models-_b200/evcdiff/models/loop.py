@@ -10,7 +10,7 @@ single CUDA graph per key and replayed; inputs are copied into the static buffer
 """
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from .._lib import EvcError, PndmCoef
 
 
@@ -48,6 +48,9 @@ class SamplerLoop:
 
     def _capture_or_run(self, key, body, graph):
         """body() enqueues the loop on the current stream.  With graph=True it is captured once and replayed."""
+        # small batches are launch-latency bound: overlap kernel prologues with programmatic dependent launch
+        pixels = self.x.shape[0] * self.x.shape[2] * self.x.shape[3]
+        _lib.load().evc_set_pdl(1 if pixels <= 8 * 128 * 128 else 0)
         if not graph:
             n0 = ops.launch_count()
             body()

@@ -38,6 +38,9 @@ enum evc_status {
 
 int evc_version(void);
 const char* evc_last_error(void);
+/* Launch the kernels of the sampling loop with programmatic dependent launch (the prologue of kernel N+1 overlaps the
+ * tail of kernel N).  Pays off for small, launch-latency-bound batches.  The EVC_PDL environment variable overrides. */
+void evc_set_pdl(int enabled);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t evc_launch_count(void);
 
