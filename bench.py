@@ -164,7 +164,7 @@ def workload_config(args, world):
                         f"{args.sampler.upper()}-{args.subsample} ({EVALS[args.sampler](args.subsample)} UNet evaluations per "
                         f"cycle), {MODEL_NAME[args.model]}, random init, 5 predicted 128x128 frames per "
                         f"video per step",
-            "model": args.model,
+            "model": args.model, "precision": args.precision,
             "videos_per_gpu": args.videos, "sampler": args.sampler, "subsample": args.subsample,
             "micro_batch": args.micro_batch, "parallelism": f"shard-by-video x{world}, one NCCL gather per step",
             "l2": "working set (>= 2 GB of activations per evaluation) exceeds the 126 MB L2; no explicit flush"}
@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--subsample", type=int, default=100)
     ap.add_argument("--model", default="ncsnpp", choices=["ncsnpp", "unet_deep", "unet_deeper"],
                     help="ncsnpp = BASELINE configs[1-4]; unet_* = configs[4] (models/unet.py variant)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16 (default, the metric's dtype) | fp32 = split-bf16 x3 arithmetic (1e-3 tolerance mode)")
     ap.add_argument("--ref-evals", type=int, default=4)
     ap.add_argument("--cpu-evals", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,6 +218,7 @@ def main():
         from evcdiff.models.unet import UNet_DDPM
         cfg.mode = "deep" if args.model == "unet_deep" else "deeper"
         net = UNet_DDPM(cfg).to(dev).eval()
+    net.precision = args.precision
 
     videos = synthetic_videos(args.videos, seed=rank)
     data = torch.from_numpy(videos[:, :2].reshape(args.videos, 6, 128, 128)).double() / 255.0  # city_sender.py:487
@@ -335,8 +338,9 @@ def main():
                              f"the reference, {cores} host threads), extrapolated x101; {spe:.3f} s/evaluation"}
         line = {"metric": "predicted frames/s (128x128)", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(args, world), "clocks": clk,
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (split hi/lo operands, fp32 accumulate)",
+                "data": "synthetic", "config": workload_config(args, world), "clocks": clk,
                 "e2e": {"value": e2e, "unit": "frames/s",
                         "h2d_bytes_per_step": host_in.numel() * host_in.element_size(),
                         "d2h_bytes_per_step": host_out.numel() * host_out.element_size()},

@@ -28,6 +28,23 @@ __device__ __forceinline__ float silu_f(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
   return x * r;
 }
+// split-precision pair (hi, lo) <-> fp32: x = hi + lo, hi = bf16(x), lo = bf16(x - hi)
+__device__ __forceinline__ void split8(const float (&f)[8], uint4& hi, uint4& lo) {
+  float g[8];
+  hi = pack8(f);
+  float h[8];
+  unpack8(hi, h);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = f[j] - h[j];
+  lo = pack8(g);
+}
+__device__ __forceinline__ void add8(const uint4& lo, float (&f)[8]) {
+  float g[8];
+  unpack8(lo, g);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] += g[j];
+}
+
 // read-only 16-byte load that allocates in L1 (FIR stencils: every input vector is re-read by 4-9 neighbouring threads)
 __device__ __forceinline__ uint4 ld_ro16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 // streaming 16-byte load (read once: do not pollute L1)
@@ -47,7 +64,7 @@ __device__ __forceinline__ uint4 ld_nc16(const void* p) {
 // ---------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C,
                                 long long* __restrict__ stats, int c_total, int c_off, int pix_per_block,
-                                float* __restrict__ partials, unsigned* __restrict__ tickets) {
+                                float* __restrict__ partials, unsigned* __restrict__ tickets, long long x_lo_off) {
   extern __shared__ float sred[];  // [rows][nvec][16]
   __shared__ unsigned s_last;
   pdl_wait();
@@ -74,6 +91,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
       for (int k = 0; k < 4; ++k) {
         float f[8];
         unpack8(u[k], f);
+        if (x_lo_off != 0) add8(ld_nc16(xb + x_lo_off + (long long)(p + k * rows) * ldx), f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           s[j] += f[j];
@@ -84,6 +102,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
     for (; p < p_end; p += rows) {
       float f[8];
       unpack8(ld_nc16(xb + (long long)p * ldx), f);
+      if (x_lo_off != 0) add8(ld_nc16(xb + x_lo_off + (long long)p * ldx), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s[j] += f[j];
@@ -144,7 +163,10 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
                                                        const long long* __restrict__ stats0,
                                                        const long long* __restrict__ stats1, int groups, float eps,
                                                        const float* __restrict__ ss, int adagn,
-                                                       __nv_bfloat16* __restrict__ y, int pix_per_block) {
+                                                       __nv_bfloat16* __restrict__ y, int pix_per_block,
+                                                       const __nv_bfloat16* __restrict__ x0_lo,
+                                                       const __nv_bfloat16* __restrict__ x1_lo,
+                                                       __nv_bfloat16* __restrict__ y_lo) {
   __shared__ float s_mean[64], s_rstd[64];
   __shared__ float s_ps[64][9], s_pq[64][9];
   pdl_wait();
@@ -201,6 +223,28 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
   const int p0 = p_begin + threadIdx.y;
   const __nv_bfloat16* src = (first ? x0 + c : x1 + (c - C0)) + ((long long)b * HW + p0) * ld;
   __nv_bfloat16* dst = y + ((long long)b * HW + p0) * C + c;
+  if (y_lo != nullptr) {
+    // split-precision path (accuracy mode, not tuned): x = hi + lo in, (hi, lo) out
+    const __nv_bfloat16* src_lo = (first ? x0_lo + c : x1_lo + (c - C0)) + ((long long)b * HW + p0) * ld;
+    __nv_bfloat16* dst_lo = y_lo + ((long long)b * HW + p0) * C + c;
+    const long long ss1 = (long long)rows * ld, ds1 = (long long)rows * C;
+    for (int p = p0; p < p_end; p += rows) {
+      float f[8];
+      unpack8(ld_nc16(src), f);
+      add8(ld_nc16(src_lo), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(f[j], a[j], bb[j]);
+        f[j] = SILU ? t / (1.f + expf(-t)) : t;
+      }
+      uint4 hi, lo;
+      split8(f, hi, lo);
+      *reinterpret_cast<uint4*>(dst) = hi;
+      *reinterpret_cast<uint4*>(dst_lo) = lo;
+      src += ss1; src_lo += ss1; dst += ds1; dst_lo += ds1;
+    }
+    return;
+  }
   const long long sstep = (long long)rows * ld, dstep = (long long)rows * C;
   int n = (p0 < p_end) ? (p_end - p0 + rows - 1) / rows : 0;  // pixels this thread handles
   // software pipeline: the loads of the next four pixels are in flight while the current four are normalised
@@ -255,10 +299,29 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
 //   down: out[i]    = (x[2i-1] + 3 x[2i] + 3 x[2i+1] + x[2i+2]) / 8                  (per axis)
 // One thread = one output pixel x 8 channels.
 // ---------------------------------------------------------------------------------------------
+// Loads / stores of one 8-channel vector; in split-precision mode the value is hi + lo and is written back as a pair.
+template <bool SPLIT>
+__device__ __forceinline__ void fir_load(const __nv_bfloat16* p, long long lo_off, float (&f)[8]) {
+  unpack8(ld_ro16(p), f);
+  if (SPLIT) add8(ld_ro16(p + lo_off), f);
+}
+template <bool SPLIT>
+__device__ __forceinline__ void fir_store(__nv_bfloat16* p, long long lo_off, const float (&f)[8]) {
+  if (SPLIT) {
+    uint4 hi, lo;
+    split8(f, hi, lo);
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + lo_off) = lo;
+  } else {
+    *reinterpret_cast<uint4*>(p) = pack8(f);
+  }
+}
+
 // One thread = one INPUT pixel x 8 channels -> the 2x2 output pixels it expands to (3x3 input neighbourhood,
 // 9 loads for 4 stores instead of 16).  Horizontal pass first: L = (x[i-1] + 3 x[i]) / 4, R = (3 x[i] + x[i+1]) / 4.
+template <bool SPLIT>
 __global__ void fir_up_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W,
-                              int C) {
+                              int C, long long x_lo_off, long long y_lo_off) {
   pdl_wait();
   pdl_trigger();
   const int nvec = C / 8;
@@ -283,13 +346,13 @@ __global__ void fir_up_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
       }
       const __nv_bfloat16* row = xb + (long long)yy * W * C;
       float c0[8], cm[8], cp[8];
-      unpack8(ld_ro16(row + (long long)ix * C), c0);
-      if (ix > 0) unpack8(ld_ro16(row + (long long)(ix - 1) * C), cm);
+      fir_load<SPLIT>(row + (long long)ix * C, x_lo_off, c0);
+      if (ix > 0) fir_load<SPLIT>(row + (long long)(ix - 1) * C, x_lo_off, cm);
       else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) cm[j] = 0.f;
       }
-      if (ix + 1 < W) unpack8(ld_ro16(row + (long long)(ix + 1) * C), cp);
+      if (ix + 1 < W) fir_load<SPLIT>(row + (long long)(ix + 1) * C, x_lo_off, cp);
       else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) cp[j] = 0.f;
@@ -304,21 +367,22 @@ __global__ void fir_up_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
     __nv_bfloat16* yb = y + (((long long)b * 2 * H + 2 * iy) * OW + 2 * ix) * C + v * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = 0.25f * hl[0][j] + 0.75f * hl[1][j];
-    *reinterpret_cast<uint4*>(yb) = pack8(o);
+    fir_store<SPLIT>(yb, y_lo_off, o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = 0.25f * hr[0][j] + 0.75f * hr[1][j];
-    *reinterpret_cast<uint4*>(yb + C) = pack8(o);
+    fir_store<SPLIT>(yb + C, y_lo_off, o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = 0.75f * hl[1][j] + 0.25f * hl[2][j];
-    *reinterpret_cast<uint4*>(yb + (long long)OW * C) = pack8(o);
+    fir_store<SPLIT>(yb + (long long)OW * C, y_lo_off, o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = 0.75f * hr[1][j] + 0.25f * hr[2][j];
-    *reinterpret_cast<uint4*>(yb + (long long)OW * C + C) = pack8(o);
+    fir_store<SPLIT>(yb + (long long)OW * C + C, y_lo_off, o);
   }
 }
 
+template <bool SPLIT>
 __global__ void fir_down_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
-                                int W, int C) {
+                                int W, int C, long long x_lo_off, long long y_lo_off) {
   pdl_wait();
   pdl_trigger();
   const int nvec = C / 8;
@@ -345,14 +409,13 @@ __global__ void fir_down_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
         const int xx = 2 * ox - 1 + c;
         if (xx < 0 || xx >= W) continue;
         const float w = k[a] * k[c];
-        const uint4 u = ld_ro16(xb + ((long long)yy * W + xx) * C);
         float f[8];
-        unpack8(u, f);
+        fir_load<SPLIT>(xb + ((long long)yy * W + xx) * C, x_lo_off, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, f[j], acc[j]);
       }
     }
-    *reinterpret_cast<uint4*>(y + (((long long)b * OH + oy) * OW + ox) * C + v * 8) = pack8(acc);
+    fir_store<SPLIT>(y + (((long long)b * OH + oy) * OW + ox) * C + v * 8, y_lo_off, acc);
   }
 }
 
@@ -377,7 +440,7 @@ __global__ void nearest_up2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 // Row softmax: one warp per row, fp32 in, bf16 out.  cols % 4 == 0.
 // ---------------------------------------------------------------------------------------------
 __global__ void softmax_rows_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, long long rows,
-                                    int cols) {
+                                    int cols, __nv_bfloat16* __restrict__ P_lo) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -398,10 +461,18 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, __nv_bfloat16* 
   const float inv = 1.f / sum;
   for (int c = lane * 4; c < cols; c += 128) {
     const float4 v = *reinterpret_cast<const float4*>(s + c);
+    const float e0 = __expf(v.x - m) * inv, e1 = __expf(v.y - m) * inv, e2 = __expf(v.z - m) * inv,
+                e3 = __expf(v.w - m) * inv;
     uint2 o;
-    o.x = pack_bf16x2(__expf(v.x - m) * inv, __expf(v.y - m) * inv);
-    o.y = pack_bf16x2(__expf(v.z - m) * inv, __expf(v.w - m) * inv);
+    o.x = pack_bf16x2(e0, e1);
+    o.y = pack_bf16x2(e2, e3);
     *reinterpret_cast<uint2*>(p + c) = o;
+    if (P_lo != nullptr) {
+      uint2 l;
+      l.x = pack_bf16x2(e0 - bf16_lo(o.x), e1 - bf16_hi(o.x));
+      l.y = pack_bf16x2(e2 - bf16_lo(o.y), e3 - bf16_hi(o.y));
+      *reinterpret_cast<uint2*>(P_lo + row * cols + c) = l;
+    }
   }
 }
 
@@ -411,7 +482,8 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, __nv_bfloat16* 
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void pack_nchw_kernel(const T* __restrict__ src, int B, int C, int HW, float scale, float shift,
-                                 __nv_bfloat16* __restrict__ dst, int Cpad, int c_off) {
+                                 __nv_bfloat16* __restrict__ dst, int Cpad, int c_off,
+                                 __nv_bfloat16* __restrict__ dst_lo) {
   const long long total = (long long)B * HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / HW);
@@ -421,7 +493,10 @@ __global__ void pack_nchw_kernel(const T* __restrict__ src, int B, int C, int HW
     // evaluated in the source precision with separate multiply / add, like the reference's `2 * X - 1.`
     for (int c = 0; c < C; ++c) {
       const T v = s[(long long)c * HW] * (T)scale;
-      d[c] = __float2bfloat16_rn((float)(v + (T)shift));
+      const float f = (float)(v + (T)shift);
+      const __nv_bfloat16 h = __float2bfloat16_rn(f);
+      d[c] = h;
+      if (dst_lo != nullptr) dst_lo[i * Cpad + c_off + c] = __float2bfloat16_rn(f - __bfloat162float(h));
     }
   }
 }
@@ -455,9 +530,21 @@ extern "C" int evc_gn_stats_workspace(int32_t B, int32_t HW, int32_t C, int64_t*
   return EVC_OK;
 }
 
+static int gn_stats_impl(const void* x, const void* x_lo, int64_t ldx, int32_t B, int32_t HW, int32_t C, int64_t* stats,
+                         int32_t c_total, int32_t c_off, void* workspace, int64_t workspace_bytes, evc_stream_t stream);
 extern "C" int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, int64_t* stats,
                             int32_t c_total, int32_t c_off, void* workspace, int64_t workspace_bytes,
                             evc_stream_t stream) {
+  return gn_stats_impl(x, nullptr, ldx, B, HW, C, stats, c_total, c_off, workspace, workspace_bytes, stream);
+}
+extern "C" int evc_gn_stats_split(const void* x, const void* x_lo, int64_t ldx, int32_t B, int32_t HW, int32_t C,
+                                  int64_t* stats, int32_t c_total, int32_t c_off, void* workspace,
+                                  int64_t workspace_bytes, evc_stream_t stream) {
+  if (!x_lo) return evc_set_error(EVC_ERR_INVALID, "evc_gn_stats_split: missing residual plane");
+  return gn_stats_impl(x, x_lo, ldx, B, HW, C, stats, c_total, c_off, workspace, workspace_bytes, stream);
+}
+static int gn_stats_impl(const void* x, const void* x_lo, int64_t ldx, int32_t B, int32_t HW, int32_t C, int64_t* stats,
+                         int32_t c_total, int32_t c_off, void* workspace, int64_t workspace_bytes, evc_stream_t stream) {
   if (!x || !stats || !workspace || B < 1 || HW < 1 || C < 8 || (C % 8) || (ldx % 8) || (c_off % 8))
     return evc_set_error(EVC_ERR_INVALID, "evc_gn_stats: bad arguments");
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15))
@@ -484,14 +571,35 @@ extern "C" int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, i
   const size_t smem = (size_t)rows * nvec * 16 * sizeof(float);
   cudaError_t le = evc_launch(gn_stats_kernel, grid, block, smem, (cudaStream_t)stream, 1,
                               reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (int)HW, (int)C,
-                              reinterpret_cast<long long*>(stats), (int)c_total, (int)c_off, ppb, partials, tickets);
+                              reinterpret_cast<long long*>(stats), (int)c_total, (int)c_off, ppb, partials, tickets,
+                              (long long)(x_lo ? reinterpret_cast<const __nv_bfloat16*>(x_lo) - reinterpret_cast<const __nv_bfloat16*>(x) : 0));
   if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
   return evc_check_launch("gn_stats_kernel");
 }
 
+static int gn_apply_impl(const void* x0, const void* x0_lo, int32_t C0, const void* x1, const void* x1_lo, int32_t C1,
+                         int32_t B, int32_t HW, const int64_t* stats0, const int64_t* stats1, int32_t groups, float eps,
+                         const float* ss, int32_t adagn, int32_t silu, void* y, void* y_lo, evc_stream_t stream);
+
 extern "C" int evc_gn_apply(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int32_t HW,
                             const int64_t* stats0, const int64_t* stats1, int32_t groups, float eps, const float* ss,
                             int32_t adagn, int32_t silu, void* y, evc_stream_t stream) {
+  return gn_apply_impl(x0, nullptr, C0, x1, nullptr, C1, B, HW, stats0, stats1, groups, eps, ss, adagn, silu, y, nullptr,
+                       stream);
+}
+
+extern "C" int evc_gn_apply_split(const void* x0, const void* x0_lo, int32_t C0, const void* x1, const void* x1_lo,
+                                  int32_t C1, int32_t B, int32_t HW, const int64_t* stats0, const int64_t* stats1,
+                                  int32_t groups, float eps, const float* ss, int32_t adagn, int32_t silu, void* y,
+                                  void* y_lo, evc_stream_t stream) {
+  if (!x0_lo || !y_lo || (x1 != nullptr && x1_lo == nullptr))
+    return evc_set_error(EVC_ERR_INVALID, "evc_gn_apply_split: missing residual planes");
+  return gn_apply_impl(x0, x0_lo, C0, x1, x1_lo, C1, B, HW, stats0, stats1, groups, eps, ss, adagn, silu, y, y_lo, stream);
+}
+
+static int gn_apply_impl(const void* x0, const void* x0_lo, int32_t C0, const void* x1, const void* x1_lo, int32_t C1,
+                         int32_t B, int32_t HW, const int64_t* stats0, const int64_t* stats1, int32_t groups, float eps,
+                         const float* ss, int32_t adagn, int32_t silu, void* y, void* y_lo, evc_stream_t stream) {
   if (!x0 || !stats0 || (x1 != nullptr && stats1 == nullptr) || !ss || !y || B < 1 || HW < 1 || C0 < 8 || (C0 % 8) || (C1 % 8) || (x1 == nullptr && C1 != 0) ||
       groups < 1 || ((C0 + C1) % groups))
     return evc_set_error(EVC_ERR_INVALID, "evc_gn_apply: bad arguments");
@@ -512,23 +620,39 @@ extern "C" int evc_gn_apply(const void* x0, int32_t C0, const void* x1, int32_t 
                               reinterpret_cast<const __nv_bfloat16*>(x0), (int)C0, reinterpret_cast<const __nv_bfloat16*>(x1),
                               (int)C1, (int)HW, reinterpret_cast<const long long*>(stats0),
                               reinterpret_cast<const long long*>(stats1), (int)groups, eps, ss, (int)adagn,
-                              reinterpret_cast<__nv_bfloat16*>(y), ppb);
+                              reinterpret_cast<__nv_bfloat16*>(y), ppb, reinterpret_cast<const __nv_bfloat16*>(x0_lo),
+                              reinterpret_cast<const __nv_bfloat16*>(x1_lo), reinterpret_cast<__nv_bfloat16*>(y_lo));
   if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
   return evc_check_launch("gn_apply_kernel");
 }
 
-extern "C" int evc_fir_resample(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, int32_t up,
-                                evc_stream_t stream) {
-  if (!x || !y || B < 1 || H < 1 || W < 1 || C < 8 || (C % 8) || (!up && ((H | W) & 1)))
+static int fir_impl(const void* x, const void* x_lo, void* y, void* y_lo, int32_t B, int32_t H, int32_t W, int32_t C,
+                    int32_t up, evc_stream_t stream) {
+  if (!x || !y || B < 1 || H < 1 || W < 1 || C < 8 || (C % 8) || (!up && ((H | W) & 1)) || ((x_lo != nullptr) != (y_lo != nullptr)))
     return evc_set_error(EVC_ERR_INVALID, "evc_fir_resample: bad arguments");
   const long long work = up ? (long long)B * H * W : (long long)B * (H / 2) * (W / 2);  // threads: input px (up) / output px
   const long long items = work * (C / 8);
   const int grid = grid_for(items, 256);
-  cudaError_t le = evc_launch(up ? fir_up_kernel : fir_down_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 1,
+  const bool split = (x_lo != nullptr);
+  const long long xo = split ? reinterpret_cast<const __nv_bfloat16*>(x_lo) - reinterpret_cast<const __nv_bfloat16*>(x) : 0;
+  const long long yo = split ? reinterpret_cast<__nv_bfloat16*>(y_lo) - reinterpret_cast<__nv_bfloat16*>(y) : 0;
+  auto kern = up ? (split ? fir_up_kernel<true> : fir_up_kernel<false>) : (split ? fir_down_kernel<true> : fir_down_kernel<false>);
+  cudaError_t le = evc_launch(kern, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 1,
                               reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), (int)B, (int)H,
-                              (int)W, (int)C);
+                              (int)W, (int)C, xo, yo);
   if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
   return evc_check_launch("fir_resample");
+}
+
+extern "C" int evc_fir_resample(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, int32_t up,
+                                evc_stream_t stream) {
+  return fir_impl(x, nullptr, y, nullptr, B, H, W, C, up, stream);
+}
+
+extern "C" int evc_fir_resample_split(const void* x, const void* x_lo, void* y, void* y_lo, int32_t B, int32_t H,
+                                      int32_t W, int32_t C, int32_t up, evc_stream_t stream) {
+  if (!x_lo || !y_lo) return evc_set_error(EVC_ERR_INVALID, "evc_fir_resample_split: missing residual planes");
+  return fir_impl(x, x_lo, y, y_lo, B, H, W, C, up, stream);
 }
 
 extern "C" int evc_nearest_up2(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
@@ -541,29 +665,41 @@ extern "C" int evc_nearest_up2(const void* x, void* y, int32_t B, int32_t H, int
   return evc_check_launch("nearest_up2_kernel");
 }
 
+extern "C" int evc_softmax_rows_split(const float* S, void* P, void* P_lo, int64_t rows, int32_t cols,
+                                      evc_stream_t stream);
 extern "C" int evc_softmax_rows(const float* S, void* P, int64_t rows, int32_t cols, evc_stream_t stream) {
+  return evc_softmax_rows_split(S, P, nullptr, rows, cols, stream);
+}
+extern "C" int evc_softmax_rows_split(const float* S, void* P, void* P_lo, int64_t rows, int32_t cols,
+                                      evc_stream_t stream) {
   if (!S || !P || rows < 1 || cols < 4 || (cols % 4)) return evc_set_error(EVC_ERR_INVALID, "evc_softmax_rows: bad arguments");
   const int warps = 8;
   const long long grid = (rows + warps - 1) / warps;
   if (grid > 0x7fffffffLL) return evc_set_error(EVC_ERR_INVALID, "evc_softmax_rows: too many rows");
   softmax_rows_kernel<<<(unsigned)grid, warps * 32, 0, (cudaStream_t)stream>>>(S, reinterpret_cast<__nv_bfloat16*>(P),
-                                                                              rows, cols);
+                                                                              rows, cols, reinterpret_cast<__nv_bfloat16*>(P_lo));
   return evc_check_launch("softmax_rows_kernel");
 }
 
+extern "C" int evc_pack_nchw_split(const void* src, int32_t src_is_f64, int32_t B, int32_t C, int32_t HW, float scale,
+                                   float shift, void* dst, void* dst_lo, int32_t Cpad, int32_t c_off, evc_stream_t stream);
 extern "C" int evc_pack_nchw(const void* src, int32_t src_is_f64, int32_t B, int32_t C, int32_t HW, float scale,
                              float shift, void* dst, int32_t Cpad, int32_t c_off, evc_stream_t stream) {
+  return evc_pack_nchw_split(src, src_is_f64, B, C, HW, scale, shift, dst, nullptr, Cpad, c_off, stream);
+}
+extern "C" int evc_pack_nchw_split(const void* src, int32_t src_is_f64, int32_t B, int32_t C, int32_t HW, float scale,
+                                   float shift, void* dst, void* dst_lo, int32_t Cpad, int32_t c_off, evc_stream_t stream) {
   if (!src || !dst || B < 1 || C < 1 || HW < 1 || c_off < 0 || c_off + C > Cpad)
     return evc_set_error(EVC_ERR_INVALID, "evc_pack_nchw: bad arguments");
   const int grid = grid_for((long long)B * HW, 256);
   if (src_is_f64)
     pack_nchw_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(src), B, C, HW,
                                                                      scale, shift, reinterpret_cast<__nv_bfloat16*>(dst),
-                                                                     Cpad, c_off);
+                                                                     Cpad, c_off, reinterpret_cast<__nv_bfloat16*>(dst_lo));
   else
     pack_nchw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(src), B, C, HW, scale,
                                                                     shift, reinterpret_cast<__nv_bfloat16*>(dst), Cpad,
-                                                                    c_off);
+                                                                    c_off, reinterpret_cast<__nv_bfloat16*>(dst_lo));
   return evc_check_launch("pack_nchw_kernel");
 }
 

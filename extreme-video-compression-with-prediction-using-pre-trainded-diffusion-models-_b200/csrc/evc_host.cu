@@ -17,6 +17,16 @@ int evc_set_error(int code, const char* msg) {
 extern "C" const char* evc_last_error(void) { return g_err; }
 extern "C" int evc_version(void) { return 1; }
 extern "C" int64_t evc_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" int64_t evc_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(evc_tensor4);
+    case 1: return sizeof(evc_gemm_desc);
+    case 2: return sizeof(evc_attn_desc);
+    case 3: return sizeof(evc_step_coef);
+    case 4: return sizeof(evc_pndm_coef);
+    default: return -1;
+  }
+}
 
 int evc_check_launch(const char* what) {
   g_launches.fetch_add(1);

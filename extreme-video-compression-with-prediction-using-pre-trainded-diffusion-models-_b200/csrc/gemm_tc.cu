@@ -22,13 +22,21 @@ constexpr int kThreads = 128 + kEpiThreads;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 
+constexpr int kMaxVSeg = 9;
+
+// Split-precision ("fp32-tolerance") mode: every bf16 tensor has a second bf16 plane holding the rounding residual
+// (x = hi + lo carries 16 mantissa bits) and a product is evaluated as hi*hi + hi*lo + lo*hi in the fp32 accumulator.
+// In the K loop this is simply three "virtual segments" per source segment: (A_hi, W_hi), (A_hi, W_lo), (A_lo, W_hi).
 struct alignas(64) GemmParams {
-  CUtensorMap a_map[3];
-  CUtensorMap b_map;
-  int n_seg;
-  int seg_taps[3];
-  int seg_kb[3];  // 64-channel blocks per tap (last one may be partial: TMA zero-fills the A columns)
-  int seg_c[3];   // channels per tap
+  CUtensorMap a_map[6];  // [0,3) hi planes of the source segments, [3,6) lo planes
+  CUtensorMap b_map[2];  // W hi, W lo
+  int n_seg;             // number of virtual segments
+  int seg_a[kMaxVSeg];   // a_map index
+  int seg_b[kMaxVSeg];   // b_map index
+  int seg_koff[kMaxVSeg];  // first W column of the source segment
+  int seg_taps[kMaxVSeg];
+  int seg_kb[kMaxVSeg];  // 64-channel blocks per tap (last one may be partial: TMA zero-fills the A columns)
+  int seg_c[kMaxVSeg];   // channels per tap
   int B, H, W;
   int TW, TH, TB;
   int tiles_x, tiles_y, tiles_b, tiles_n;
@@ -40,8 +48,10 @@ struct alignas(64) GemmParams {
   int out_mode;
   long long out_ld, out_bs;
   void* out;
+  void* out_lo;  // split mode: residual plane of a bf16 output (NULL otherwise)
   const float* bias;
   const __nv_bfloat16* resid;
+  const __nv_bfloat16* resid_lo;
   long long resid_ld;
   float alpha;
   unsigned tx_bytes;
@@ -88,13 +98,12 @@ __device__ __forceinline__ void stat_add(long long* dst, float v) {
   atomicAdd(reinterpret_cast<unsigned long long*>(dst), static_cast<unsigned long long>(__float2ll_rn(v * kStatScale)));
 }
 
-template <typename T>
 __device__ __forceinline__ void store_chunk(const GemmParams& p, const float (&f)[32], int ncols, int n, long long pix,
-                                            int b, long long pin) {
+                                            int b, long long pin, void* out_base) {
   // f[0..ncols) are final values for output columns n..n+ncols of pixel row `pix` (global row index),
   // `pin` = pixel index inside sample b.
   if (p.out_mode == EVC_OUT_BF16_ROWS) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + n;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_base) + pix * p.out_ld + n;
     if (n + ncols <= p.N && (p.N & 7) == 0 && (p.out_ld & 7) == 0) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
@@ -113,7 +122,7 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, const float (&f
         if (j < ncols && n + j < p.N) o[j] = __float2bfloat16_rn(f[j]);
     }
   } else if (p.out_mode == EVC_OUT_F32_ROWS) {
-    float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + n;
+    float* o = reinterpret_cast<float*>(out_base) + pix * p.out_ld + n;
     if (n + ncols <= p.N && (p.N & 3) == 0 && (p.out_ld & 3) == 0) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -125,12 +134,12 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, const float (&f
         if (j < ncols && n + j < p.N) o[j] = f[j];
     }
   } else if (p.out_mode == EVC_OUT_BF16_T) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)b * p.out_bs + pin;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_base) + (long long)b * p.out_bs + pin;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (j < ncols && n + j < p.N) o[(long long)(n + j) * p.out_ld] = __float2bfloat16_rn(f[j]);
   } else {
-    float* o = reinterpret_cast<float*>(p.out) + (long long)b * p.out_bs + pin;
+    float* o = reinterpret_cast<float*>(out_base) + (long long)b * p.out_bs + pin;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (j < ncols && n + j < p.N) o[(long long)(n + j) * p.out_ld] = f[j];
@@ -157,8 +166,9 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.n_seg; ++s) tma_prefetch_desc(&p.a_map[s]);
-    tma_prefetch_desc(&p.b_map);
+    for (int s = 0; s < p.n_seg; ++s) tma_prefetch_desc(&p.a_map[p.seg_a[s]]);
+    tma_prefetch_desc(&p.b_map[0]);
+    if (p.out_lo != nullptr) tma_prefetch_desc(&p.b_map[1]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
@@ -196,11 +206,12 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       decode_tile<CG>(p, tile, rank, x0, y0, b0, n0);
       const int zb = p.b_batched ? b0 : 0;
       const int nb = n0 + rank * (p.BN / CG);  // this CTA's half of the B tile
-      int kbase = 0;
       for (int s = 0; s < p.n_seg; ++s) {
         const int taps = p.seg_taps[s];
+        const CUtensorMap* am = &p.a_map[p.seg_a[s]];
+        const CUtensorMap* bm = &p.b_map[p.seg_b[s]];
         for (int t = 0; t < taps; ++t) {
-          const int ktap = kbase + t * p.seg_c[s];
+          const int ktap = p.seg_koff[s] + t * p.seg_c[s];
           const int dy = (taps == 9) ? (t / 3 - 1) : 0;
           const int dx = (taps == 9) ? (t % 3 - 1) : 0;
           for (int c = 0; c < p.seg_kb[s]; ++c) {
@@ -210,12 +221,12 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
               // both CTAs' bytes land on the leader's barrier; the peer contributes a plain (remote) arrival
               if (rank == 0) mbar_expect_tx(full_bar(stage), p.tx_bytes * 2u);
               else mbar_arrive_cluster(full_bar(stage), 0);
-              tma_load_4d_2sm(&p.a_map[s], sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
-              tma_load_3d_2sm(&p.b_map, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
+              tma_load_4d_2sm(am, sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
+              tma_load_3d_2sm(bm, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
             } else {
               mbar_expect_tx(full_bar(stage), p.tx_bytes);
-              tma_load_4d(&p.a_map[s], sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
-              tma_load_3d(&p.b_map, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
+              tma_load_4d(am, sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
+              tma_load_3d(bm, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
             }
             if (++stage == p.num_stages) {
               stage = 0;
@@ -223,7 +234,6 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
             }
           }
         }
-        kbase += taps * p.seg_c[s];
       }
     }
   } else if (warp == 1 && lane == 0 && rank == 0) {
@@ -371,17 +381,32 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (j < ncols && n + j < p.N) f[j] += __bfloat162float(r[j]);
+            if (p.resid_lo != nullptr) {
+              const __nv_bfloat16* r2 = p.resid_lo + pix * p.resid_ld + n;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols && n + j < p.N) f[j] += __bfloat162float(r2[j]);
+            }
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
-          store_chunk<float>(p, f, ncols, n, pix, b, pin);
+          store_chunk(p, f, ncols, n, pix, b, pin, p.out);
+          if (p.out_lo != nullptr) {
+            float g[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) g[j] = f[j] - __bfloat162float(__float2bfloat16_rn(f[j]));
+            store_chunk(p, g, ncols, n, pix, b, pin, p.out_lo);
+          }
         }
         if (p.stats != nullptr) {
           // statistics of the values as stored (bf16-rounded); rows outside the tensor contribute zero
           float sq[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float r = (valid && j < ncols && n + j < p.N) ? __bfloat162float(__float2bfloat16_rn(f[j])) : 0.f;
+            // bf16 mode: the value as stored; split mode: hi + lo represents f to 2^-17, use f itself
+            const float r = (valid && j < ncols && n + j < p.N)
+                                ? (p.out_lo != nullptr ? f[j] : __bfloat162float(__float2bfloat16_rn(f[j])))
+                                : 0.f;
             f[j] = r;
             sq[j] = r * r;
           }
@@ -482,7 +507,6 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   evc_gemm_plan* pl = new evc_gemm_plan();
   GemmParams& p = pl->p;
   memset(&p, 0, sizeof(p));
-  p.n_seg = d->n_seg;
   p.B = d->B;
   p.H = d->H;
   p.W = d->W;
@@ -536,34 +560,60 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   p.stride = cs;
   int total_kb = 0;
   long long ktot = 0;
+  // split precision: all-or-nothing (every A segment and W carry a residual plane)
+  const bool split = (d->w_lo != nullptr);
   for (int s = 0; s < d->n_seg; ++s) {
-    const evc_tensor4& a = d->a[s];
+    if ((d->a_lo[s].ptr != nullptr) != split) {
+      delete pl;
+      return evc_set_error(EVC_ERR_INVALID, "split precision needs a_lo for every segment and w_lo (or none of them)");
+    }
+  }
+  if (!split && (d->out_lo != nullptr || d->resid_lo != nullptr)) {
+    delete pl;
+    return evc_set_error(EVC_ERR_INVALID, "out_lo / resid_lo without split-precision operands");
+  }
+  int nv = 0;
+  for (int s = 0; s < d->n_seg; ++s) {
     if (d->taps[s] != 1 && d->taps[s] != 9) {
       delete pl;
       return evc_set_error(EVC_ERR_INVALID, "taps must be 1 or 9");
     }
-    if (a.ptr == nullptr || (a.C % 8) != 0 || a.C < 8 || a.W != d->W * cs || a.H != d->H * cs || a.B != d->B) {
-      delete pl;
-      return evc_set_error(EVC_ERR_INVALID, "A segment: C % 8 != 0 or extent mismatch");
+    for (int plane = 0; plane < (split ? 2 : 1); ++plane) {
+      const evc_tensor4& a = plane == 0 ? d->a[s] : d->a_lo[s];
+      if (a.ptr == nullptr || (a.C % 8) != 0 || a.C < 8 || a.W != d->W * cs || a.H != d->H * cs || a.B != d->B ||
+          a.C != d->a[s].C) {
+        delete pl;
+        return evc_set_error(EVC_ERR_INVALID, "A segment: C % 8 != 0 or extent mismatch");
+      }
+      if ((reinterpret_cast<uintptr_t>(a.ptr) & 15) || (a.stride_w % 8) || (a.stride_h % 8) || (a.stride_b % 8)) {
+        delete pl;
+        return evc_set_error(EVC_ERR_INVALID, "A segment: pointer/strides must be 16-byte aligned");
+      }
+      uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+      uint64_t strides[3] = {(uint64_t)a.stride_w * 2, (uint64_t)a.stride_h * 2, (uint64_t)a.stride_b * 2};
+      uint32_t box[4] = {64, (uint32_t)(TW * cs), (uint32_t)(TH * cs), (uint32_t)TB};
+      int rc = encode_map(&p.a_map[plane * 3 + s], a.ptr, 4, dims, strides, box, cs);
+      if (rc != EVC_OK) {
+        delete pl;
+        return rc;
+      }
     }
-    if ((reinterpret_cast<uintptr_t>(a.ptr) & 15) || (a.stride_w % 8) || (a.stride_h % 8) || (a.stride_b % 8)) {
-      delete pl;
-      return evc_set_error(EVC_ERR_INVALID, "A segment: pointer/strides must be 16-byte aligned");
+    const int C = d->a[s].C;
+    // (A_hi, W_hi) [, (A_hi, W_lo), (A_lo, W_hi)]
+    const int combos[3][2] = {{0, 0}, {0, 1}, {1, 0}};
+    for (int c = 0; c < (split ? 3 : 1); ++c) {
+      p.seg_a[nv] = combos[c][0] * 3 + s;
+      p.seg_b[nv] = combos[c][1];
+      p.seg_koff[nv] = (int)ktot;
+      p.seg_taps[nv] = d->taps[s];
+      p.seg_kb[nv] = (C + 63) / 64;
+      p.seg_c[nv] = C;
+      total_kb += d->taps[s] * ((C + 63) / 64);
+      ++nv;
     }
-    uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
-    uint64_t strides[3] = {(uint64_t)a.stride_w * 2, (uint64_t)a.stride_h * 2, (uint64_t)a.stride_b * 2};
-    uint32_t box[4] = {64, (uint32_t)(TW * cs), (uint32_t)(TH * cs), (uint32_t)TB};
-    int rc = encode_map(&p.a_map[s], a.ptr, 4, dims, strides, box, cs);
-    if (rc != EVC_OK) {
-      delete pl;
-      return rc;
-    }
-    p.seg_taps[s] = d->taps[s];
-    p.seg_kb[s] = (a.C + 63) / 64;
-    p.seg_c[s] = a.C;
-    total_kb += d->taps[s] * ((a.C + 63) / 64);
-    ktot += (long long)d->taps[s] * a.C;
+    ktot += (long long)d->taps[s] * C;
   }
+  p.n_seg = nv;
   if (ktot != d->w_k) {
     delete pl;
     return evc_set_error(EVC_ERR_INVALID, "w_k does not match sum(taps*C) of the A segments");
@@ -579,13 +629,19 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     if (bstride % 16) bstride = ((bstride + 15) / 16) * 16;
     uint64_t strides[2] = {(uint64_t)d->w_row_stride * 2, bstride};
     uint32_t box[3] = {64, (uint32_t)(d->bn / cg), 1};
-    int rc = encode_map(&p.b_map, d->w, 3, dims, strides, box);
+    int rc = encode_map(&p.b_map[0], d->w, 3, dims, strides, box);
+    if (rc == EVC_OK && split) {
+      if (reinterpret_cast<uintptr_t>(d->w_lo) & 15) rc = evc_set_error(EVC_ERR_INVALID, "w_lo must be 16-byte aligned");
+      else rc = encode_map(&p.b_map[1], d->w_lo, 3, dims, strides, box);
+    }
     if (rc != EVC_OK) {
       delete pl;
       return rc;
     }
   }
   p.out = d->out;
+  p.out_lo = d->out_lo;
+  p.resid_lo = reinterpret_cast<const __nv_bfloat16*>(d->resid_lo);
   p.out_mode = d->out_mode;
   p.out_ld = d->out_ld;
   p.out_bs = d->out_bs;
@@ -598,7 +654,7 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
 
   const int stage_bytes = kABytes + (d->bn / cg) * 128;
   // shared memory: [stages][barriers 256 B][bias 1 KB][residual rows 128 x (2*BN + 16) B, only with a residual]
-  p.resid_smem = (d->resid != nullptr && (d->resid_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(d->resid) & 15) == 0 &&
+  p.resid_smem = (!split && d->resid != nullptr && (d->resid_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(d->resid) & 15) == 0 &&
                   (d->w_rows % 8) == 0) ? 1 : 0;
   p.stats = reinterpret_cast<long long*>(d->stats);
   p.sample_rows = TW * TH;

@@ -28,7 +28,8 @@ class GemmDesc(C.Structure):
                 ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("bn", C.c_int32),
                 ("out", C.c_void_p), ("out_mode", C.c_int32), ("out_ld", C.c_int64), ("out_bs", C.c_int64),
                 ("bias", C.c_void_p), ("resid", C.c_void_p), ("resid_ld", C.c_int64),
-                ("alpha", C.c_float), ("max_ctas", C.c_int32), ("stats", C.c_void_p), ("stride", C.c_int32), ("cta_group", C.c_int32)]
+                ("alpha", C.c_float), ("max_ctas", C.c_int32), ("stats", C.c_void_p), ("stride", C.c_int32), ("cta_group", C.c_int32),
+                ("a_lo", Tensor4 * 3), ("w_lo", C.c_void_p), ("out_lo", C.c_void_p), ("resid_lo", C.c_void_p)]
 
 
 class AttnDesc(C.Structure):
@@ -47,12 +48,15 @@ class PndmCoef(C.Structure):
                 ("d", C.c_float), ("p", C.c_float), ("q", C.c_float)]
 
 
+ABI_STRUCTS = (Tensor4, GemmDesc, AttnDesc, StepCoef, PndmCoef)  # order = evc_struct_size ids
+
 # name -> (restype, argtypes); must list every symbol include/evcdiff.h declares (tests check this).
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
     "evc_version": (C.c_int, []),
     "evc_last_error": (C.c_char_p, []),
     "evc_launch_count": (C.c_int64, []),
+    "evc_struct_size": (C.c_int64, [C.c_int]),
     "evc_set_pdl": (None, [C.c_int]),
     "evc_gemm_plan_create": (C.c_int, [C.POINTER(GemmDesc), C.POINTER(C.c_void_p)]),
     "evc_gemm_plan_launch": (C.c_int, [_vp, _vp, _vp]),
@@ -66,6 +70,12 @@ SIGNATURES = {
     "evc_gn_stats_workspace": (C.c_int, [_i32, _i32, _i32, C.POINTER(C.c_int64)]),
     "evc_gn_stats": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
     "evc_gn_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _vp, _i32, _i32, _vp, _vp]),
+    "evc_gn_stats_split": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "evc_gn_apply_split": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _vp, _i32, _i32, _vp,
+                                     _vp, _vp]),
+    "evc_fir_resample_split": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "evc_softmax_rows_split": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
+    "evc_pack_nchw_split": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _i32, _i32, _vp]),
     "evc_fir_resample": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "evc_nearest_up2": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "evc_softmax_rows": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
@@ -98,6 +108,10 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    for which, struct in enumerate(ABI_STRUCTS):
+        if lib.evc_struct_size(which) != C.sizeof(struct):
+            raise EvcError(f"ABI mismatch: {struct.__name__} is {C.sizeof(struct)} bytes here, "
+                           f"{lib.evc_struct_size(which)} in {LIB_PATH} (rebuild the library)")
     _lib = lib
     return lib
 

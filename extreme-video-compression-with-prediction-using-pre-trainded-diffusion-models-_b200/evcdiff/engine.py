@@ -33,10 +33,11 @@ def gn_groups(ch):
 
 class Act:
     """NHWC bf16 activation with lazily computed GroupNorm statistics."""
-    __slots__ = ("t", "B", "H", "W", "C", "stats")
+    __slots__ = ("t", "lo", "B", "H", "W", "C", "stats")
 
-    def __init__(self, t):
+    def __init__(self, t, lo=None):
         self.t = t
+        self.lo = lo  # split-precision residual plane (value = t + lo), None in bf16 mode
         self.B, self.H, self.W, self.C = t.shape
         self.stats = None
 
@@ -63,18 +64,30 @@ class Pool:
 
 
 def pack_conv3(w, cin_pad=None):
-    """(Cout, Cin, 3, 3) fp32 -> (Cout, 9*Cin') bf16, K = tap-major (ky,kx), channel-minor."""
+    """(Cout, Cin, 3, 3) fp32 -> (Cout, 9*Cin') fp32, K = tap-major (ky,kx), channel-minor (EngineBase.gemm rounds it to
+    bf16, or to a (hi, lo) bf16 pair in split-precision mode)."""
     co, ci, kh, kw = w.shape
-    w = w.permute(0, 2, 3, 1)  # co, ky, kx, ci
+    w = w.float().permute(0, 2, 3, 1)  # co, ky, kx, ci
     if cin_pad is not None and cin_pad != ci:
         w = torch.nn.functional.pad(w, (0, cin_pad - ci))
-    return w.reshape(co, -1).to(torch.bfloat16).contiguous()
+    return w.reshape(co, -1).contiguous()
+
+
+def split_bf16(w):
+    """fp32 -> (hi, lo) bf16 planes with hi + lo = w to 2^-17."""
+    hi = w.to(torch.bfloat16)
+    lo = (w.float() - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
 
 
 class EngineBase:
-    def __init__(self, device, B, H):
+    def __init__(self, device, B, H, precision="bf16"):
         if torch.device(device).type != "cuda":
             raise EvcError("evcdiff engines run on CUDA devices only (no CPU fallback)")
+        if precision not in ("bf16", "fp32"):
+            raise EvcError("precision must be 'bf16' (default) or 'fp32' (split-bf16 x3, fp32-tolerance mode)")
+        self.precision = precision
+        self.split = precision == "fp32"
         self.device = torch.device(device)
         self.B, self.H = B, H
         self.pool = Pool(self.device)
@@ -99,14 +112,17 @@ class EngineBase:
         self.n_launch += 1
 
     def new_act(self, H, W, C, scratch=True):
-        t = self.pool.get((self.B, H, W, C)) if scratch else torch.zeros((self.B, H, W, C), dtype=torch.bfloat16,
-                                                                         device=self.device)
-        return Act(t)
+        def one():
+            return self.pool.get((self.B, H, W, C)) if scratch else torch.zeros((self.B, H, W, C), dtype=torch.bfloat16,
+                                                                                device=self.device)
+        return Act(one(), one() if self.split else None)
 
     def release(self, *acts):
         for a in acts:
             if a is not None:
                 self.pool.put(a.t)
+                if a.lo is not None:
+                    self.pool.put(a.lo)
 
     def alloc_stats(self, a):
         n = a.B * a.C * 2
@@ -129,7 +145,7 @@ class EngineBase:
         self.ws_bytes = max(self.ws_bytes, ops.gn_stats_workspace_bytes(act.B, act.H * act.W, act.C))
 
         def run(_):
-            ops.gn_stats(act.t, act.B, act.H * act.W, act.C, act.stats, workspace=self.workspace)
+            ops.gn_stats(act.t, act.B, act.H * act.W, act.C, act.stats, workspace=self.workspace, x_lo=act.lo)
         self._op(run, "gn_stats", dict(bytes=act.t.numel() * 2))
 
     def _stats_view(self, a):
@@ -146,39 +162,53 @@ class EngineBase:
         def run(li):
             ops.gn_apply(xa.t, xa.C, xb.t if xb is not None else None, xb.C if xb is not None else 0, xa.B,
                          xa.H * xa.W, self._stats_view(xa), self._stats_view(xb) if xb is not None else None,
-                         groups, eps, ss_fn(li), adagn, silu, out.t)
+                         groups, eps, ss_fn(li), adagn, silu, out.t, x0_lo=xa.lo,
+                         x1_lo=xb.lo if xb is not None else None, y_lo=out.lo)
         self._op(run, "gn_apply", dict(bytes=out.t.numel() * 4))
 
     def gemm(self, segs, w, out_t, out_mode, out_ld, out_bs=0, bias=None, resid=None, alpha=1.0, bias_fn=None,
-             stats_of=None, stride=1):
-        """stats_of: the Act being written; when given (and the tile geometry allows it) its GroupNorm statistics
-        are accumulated by the GEMM epilogue and no separate gn_stats launch is recorded for it."""
+             stats_of=None, stride=1, w_lo=None, out_lo=None, segs_lo=None):
+        """One implicit-GEMM launch.  segs: [(Act | tensor (B,H,W,C), taps)].  w: fp32 (N,K) weights (rounded here to bf16,
+        or split into a (hi, lo) pair in split-precision mode) or a bf16 per-sample operand (B,N,K) (+ w_lo).
+        stats_of: the Act being written; when given (and the tile geometry allows it) its GroupNorm statistics are
+        accumulated by the GEMM epilogue and no separate gn_stats launch is recorded for it."""
+        if w.dtype != torch.bfloat16:  # model weights
+            if self.split:
+                w, w_lo = split_bf16(w.to(self.device))
+            else:
+                w = w.to(self.device).to(torch.bfloat16).contiguous()
+        seg_t = [(a.t if isinstance(a, Act) else a, taps) for a, taps in segs]
+        if self.split:
+            if segs_lo is None:
+                segs_lo = [a.lo for a, _ in segs]
+            assert all(x is not None for x in segs_lo) and w_lo is not None, "split precision: missing residual planes"
+            if isinstance(resid, Act):
+                resid_lo = resid.lo
+            else:
+                resid_lo = None
+            if out_lo is None and stats_of is not None:
+                out_lo = stats_of.lo
+        else:
+            segs_lo = w_lo = out_lo = resid_lo = None
         stats_t = None
         if stats_of is not None and out_mode == EVC_OUT_BF16_ROWS and self.can_fuse_stats(stats_of.H, stats_of.W):
             self.alloc_stats(stats_of)
             stats_t = ("deferred", stats_of)
         plan_args = dict(out_bs=out_bs, bias=bias, resid=resid.t if isinstance(resid, Act) else resid,
-                         resid_ld=(resid.C if isinstance(resid, Act) else 0), alpha=alpha, stride=stride)
+                         resid_ld=(resid.C if isinstance(resid, Act) else 0), alpha=alpha, stride=stride,
+                         segs_lo=segs_lo, w_lo=w_lo, out_lo=out_lo, resid_lo=resid_lo)
+        a0 = seg_t[0][0]
+        shp = tuple(a0.shape)
+        M = shp[0] * (shp[1] // stride) * (shp[2] // stride)
+        flops = 2.0 * M * w.shape[-2] * w.shape[-1]
+        self.flops += flops
+        meta = dict(flops=flops, M=M, N=w.shape[-2], K=w.shape[-1], taps=[t for _, t in segs], hw=shp[2] // stride)
         if stats_t is not None:
             # the arena does not exist yet: create the plan in finalize()
-            self._deferred.append((len(self.ops), [(a.t if isinstance(a, Act) else a, taps) for a, taps in segs], w,
-                                   out_t, out_mode, out_ld, plan_args, stats_of, bias_fn))
-            plan = None
-            flops = 2.0 * out_t.shape[0] * stats_of.H * stats_of.W * w.shape[-2] * w.shape[-1]
-            self.flops += flops
-            a0 = segs[0][0]
-            shp = tuple(a0.t.shape) if isinstance(a0, Act) else tuple(a0.shape)
-            meta = dict(flops=flops, M=shp[0] * shp[1] * shp[2], N=w.shape[-2], K=w.shape[-1],
-                        taps=[t for _, t in segs], hw=shp[2])
+            self._deferred.append((len(self.ops), seg_t, w, out_t, out_mode, out_ld, plan_args, stats_of, bias_fn))
             self._op(None, "gemm", meta)
             return None
-        plan = ops.GemmPlan([(a.t if isinstance(a, Act) else a, taps) for a, taps in segs], w, out_t, out_mode,
-                            out_ld, **plan_args)
-        self.flops += plan.flops
-        a0 = segs[0][0]
-        shp = tuple(a0.t.shape) if isinstance(a0, Act) else tuple(a0.shape)
-        meta = dict(flops=plan.flops, M=shp[0] * shp[1] * shp[2], N=w.shape[-2], K=w.shape[-1],
-                    taps=[t for _, t in segs], hw=shp[2])
+        plan = ops.GemmPlan(seg_t, w, out_t, out_mode, out_ld, **plan_args)
         if bias_fn is None:
             self._op(lambda li: plan.launch(), "gemm", meta)
         else:
@@ -188,44 +218,53 @@ class EngineBase:
     def fir(self, a, up):
         H2, W2 = (a.H * 2, a.W * 2) if up else (a.H // 2, a.W // 2)
         out = self.new_act(H2, W2, a.C)
-        self._op(lambda li: ops.fir_resample(a.t, out.t, a.B, a.H, a.W, a.C, up), "fir",
+        self._op(lambda li: ops.fir_resample(a.t, out.t, a.B, a.H, a.W, a.C, up, x_lo=a.lo, y_lo=out.lo), "fir",
                  dict(bytes=(a.t.numel() + out.t.numel()) * 2))
         return out
 
     def attn_core(self, x, ss, gn_eps, ws, bs, heads, out_alpha):
         """out = out_alpha * (x + OUT(softmax(q k^T / sqrt(d)) v)) with q,k,v = 1x1 projections of GN(x).
-        ws/bs: [Wq, Wk, Wv, Wo] as (out, in) bf16 and fp32 biases.  The softmax(QK^T)V core is the fused tcgen05
-        attention kernel (evc_attn_*) when N % 64 == 0 and the head dim is a multiple of 64 (<= 384); otherwise
-        batched GEMMs with a per-sample B operand (K, then V^T from a transposed-store epilogue) + row softmax."""
+        ws/bs: [Wq, Wk, Wv, Wo] as (out, in) fp32 and fp32 biases.  The softmax(QK^T)V core is the fused tcgen05
+        attention kernel (evc_attn_*) when N % 64 == 0 and the head dim is a multiple of 64 (<= 384); otherwise (and
+        always in split-precision mode) batched GEMMs with a per-sample B operand (K, then V^T from a transposed-store
+        epilogue) + row softmax."""
         dev = self.device
         C, N, B = x.C, x.H * x.W, self.B
         d = C // heads
         if d % 8 != 0:
             raise EvcError("attention head dim must be a multiple of 8")
-        self._keep += [ss] + list(ws) + list(bs)
+        self._keep += [ss] + list(bs)
         wq, wk, wv, wo = ws
         bq, bk, bv, bo = bs
         hn = self.new_act(x.H, x.W, C)
         self.gn_apply(x, None, lambda li: ss, gn_eps, False, False, hn)
+        sp = self.split
         qk = self.pool.get((B, x.H, x.W, 2 * C))
+        qk_lo = self.pool.get((B, x.H, x.W, 2 * C)) if sp else None
         self.gemm([(hn, 1)], torch.cat([wq, wk], 0).contiguous(), qk, EVC_OUT_BF16_ROWS, 2 * C,
-                  bias=torch.cat([bq, bk]).contiguous())
+                  bias=torch.cat([bq, bk]).contiguous(), out_lo=qk_lo)
         # key axis padded to a multiple of 8 (16-byte TMA strides); only toy shapes (N < 8) ever pad.  Pad columns:
         # S = -inf (never written by the GEMM, so softmax gives P = 0) and V^T = 0.
         Np = max(8, (N + 7) // 8 * 8)
-        fused = self.fused_attention and ops.attn_supported(N, C, heads)
-        S = Pm = None
+        fused = self.fused_attention and not sp and ops.attn_supported(N, C, heads)
+        S = Pm = Pm_lo = vT_lo = None
         if fused:
             vT = self.pool.get((B, C, N))
         elif Np == N:
             vT = self.pool.get((B, C, N))
             S = self.pool.get((B, N, N), torch.float32)
             Pm = self.pool.get((B, N, N))
+            if sp:
+                vT_lo = self.pool.get((B, C, N))
+                Pm_lo = self.pool.get((B, N, N))
         else:
             vT = torch.zeros((B, C, Np), dtype=torch.bfloat16, device=dev)
             S = torch.full((B, N, Np), float("-inf"), dtype=torch.float32, device=dev)
             Pm = torch.zeros((B, N, Np), dtype=torch.bfloat16, device=dev)
-        self.gemm([(hn, 1)], wv, vT, EVC_OUT_BF16_T, Np, out_bs=C * Np, bias=bv)
+            if sp:
+                vT_lo = torch.zeros_like(vT)
+                Pm_lo = torch.zeros_like(Pm)
+        self.gemm([(hn, 1)], wv, vT, EVC_OUT_BF16_T, Np, out_bs=C * Np, bias=bv, out_lo=vT_lo)
         o = self.new_act(x.H, x.W, C)
         qk3 = qk.view(B, N, 2 * C)
         o3 = o.t.view(B, N, C)
@@ -234,23 +273,30 @@ class EngineBase:
             self.flops += plan.flops
             self._op(lambda li, plan=plan: plan.launch(), "attn", dict(flops=plan.flops, N=N, d=d, heads=heads))
         else:
+            qk3_lo = qk_lo.view(B, N, 2 * C) if sp else None
+            o3_lo = o.lo.view(B, N, C) if sp else None
             for hd in range(heads):
                 q = qk3[:, :, hd * d:(hd + 1) * d].unsqueeze(1)  # (B,1,N,d)
                 k = qk3[:, :, C + hd * d:C + (hd + 1) * d]  # (B,N,d)  per-sample B operand
-                self.gemm([(q, 1)], k, S, EVC_OUT_F32_ROWS, Np, alpha=float(int(d) ** (-0.5)))
-                self._op(lambda li, S=S, Pm=Pm: ops.softmax_rows(S, Pm, B * N, Np), "softmax",
+                q_lo = [qk3_lo[:, :, hd * d:(hd + 1) * d].unsqueeze(1)] if sp else None
+                k_lo = qk3_lo[:, :, C + hd * d:C + (hd + 1) * d] if sp else None
+                self.gemm([(q, 1)], k, S, EVC_OUT_F32_ROWS, Np, alpha=float(int(d) ** (-0.5)), w_lo=k_lo, segs_lo=q_lo)
+                self._op(lambda li, S=S, Pm=Pm, Pl=Pm_lo: ops.softmax_rows(S, Pm, B * N, Np, P_lo=Pl), "softmax",
                          dict(bytes=B * N * Np * 6))
                 self.gemm([(Pm.view(B, 1, N, Np), 1)], vT[:, hd * d:(hd + 1) * d, :], o3[:, :, hd * d:],
-                          EVC_OUT_BF16_ROWS, C)
+                          EVC_OUT_BF16_ROWS, C, w_lo=vT_lo[:, hd * d:(hd + 1) * d, :] if sp else None,
+                          segs_lo=[Pm_lo.view(B, 1, N, Np)] if sp else None, out_lo=o3_lo[:, :, hd * d:] if sp else None)
         out = self.new_act(x.H, x.W, C, scratch=False)
         self.gemm([(o, 1)], wo, out.t, EVC_OUT_BF16_ROWS, C, bias=bo, resid=x, alpha=out_alpha, stats_of=out)
         self.pool.put(qk)
-        if fused:
-            self.pool.put(vT)
-        elif Np == N:
-            self.pool.put(vT); self.pool.put(S); self.pool.put(Pm)
+        if sp:
+            self.pool.put(qk_lo)
+        if fused or Np == N:
+            for t in (vT, S, Pm, vT_lo, Pm_lo):
+                if t is not None:
+                    self.pool.put(t)
         else:
-            self._keep += [vT, S, Pm]
+            self._keep += [t for t in (vT, S, Pm, vT_lo, Pm_lo) if t is not None]
         self.release(hn, o)
         return out
 
@@ -296,10 +342,10 @@ class EngineBase:
 class NCSNppEngine(EngineBase):
     """Launch plan of NCSNpp.forward (models/better/ncsnpp_more.py:251-392) for batch size B."""
 
-    def __init__(self, net, B, device):
+    def __init__(self, net, B, device, precision="bf16"):
         cfg = net.config
         H = cfg.data.image_size
-        super().__init__(device, B, H)
+        super().__init__(device, B, H, precision)
         self.net = net
         self.cfg = cfg
         m, d = cfg.model, cfg.data
@@ -353,8 +399,9 @@ class NCSNppEngine(EngineBase):
 
         # --- buffers
         self.xin = torch.zeros((B, H, H, CIN_PAD), dtype=torch.bfloat16, device=dev)
+        self.xin_lo = torch.zeros_like(self.xin) if self.split else None
         self.eps = torch.zeros((B, self.c_x, H, H), dtype=torch.float32, device=dev)
-        xin = Act(self.xin)
+        xin = Act(self.xin, self.xin_lo)
 
         m = self.cfg.model
         nres, nlev = m.num_res_blocks, len(m.ch_mult)
@@ -434,7 +481,7 @@ class NCSNppEngine(EngineBase):
         w1 = pack_conv3(sd[P(i) + ".Conv_1.weight"].to(dev))
         b1 = sd[P(i) + ".Conv_1.bias"].float()
         if (P(i) + ".Conv_2.weight") in sd:
-            w2 = sd[P(i) + ".Conv_2.weight"].to(dev).reshape(cout, cin).to(torch.bfloat16)
+            w2 = sd[P(i) + ".Conv_2.weight"].to(dev).float().reshape(cout, cin)
             w = torch.cat([w1, w2], dim=1).contiguous()
             bias = (b1 + sd[P(i) + ".Conv_2.bias"].float()).to(dev).contiguous()
             self._keep.append(bias)
@@ -457,7 +504,7 @@ class NCSNppEngine(EngineBase):
         heads = 1 if (self.head_ch == -1 or C < self.head_ch) else C // self.head_ch
         ss = torch.cat([sd[P(i) + ".GroupNorm_0.weight"].float(), sd[P(i) + ".GroupNorm_0.bias"].float()]).to(dev)
         # NIN: y = x @ W + b with W (in, out) -> GEMM weight rows = outputs
-        ws = [sd[P(i) + f".NIN_{j}.W"].to(dev).t().to(torch.bfloat16).contiguous() for j in range(4)]
+        ws = [sd[P(i) + f".NIN_{j}.W"].to(dev).float().t().contiguous() for j in range(4)]
         bs = [sd[P(i) + f".NIN_{j}.b"].float().to(dev).contiguous() for j in range(4)]
         out = self.attn_core(x, ss.contiguous(), 1e-6, ws, bs, heads, RSQRT2)
         self.taps[f"m{i}"] = out
@@ -486,6 +533,11 @@ class NCSNppEngine(EngineBase):
     def load_input(self, x, cond):
         """x (B,15,H,W) fp32, cond (B,6,H,W) fp32/fp64 or None -> NHWC bf16 UNet input (torch.cat of
         ncsnpp_more.py:256-257 + the fp32 cast of :293, fused with the layout change)."""
-        ops.pack_nchw(x.contiguous(), self.xin, 0)
+        ops.pack_nchw(x.contiguous(), self.xin, 0, dst_lo=self.xin_lo)
         if cond is not None:
-            ops.pack_nchw(cond.contiguous(), self.xin, self.c_x)
+            ops.pack_nchw(cond.contiguous(), self.xin, self.c_x, dst_lo=self.xin_lo)
+
+    def refresh_x(self, x):
+        """Split-precision mode: the sampler-update kernels only write the bf16 hi plane of x_t; rewrite both planes."""
+        if self.split:
+            ops.pack_nchw(x, self.xin, 0, dst_lo=self.xin_lo)

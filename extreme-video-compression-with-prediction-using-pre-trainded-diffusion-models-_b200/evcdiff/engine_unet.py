@@ -18,10 +18,10 @@ from .engine import CIN_PAD, Act, EngineBase, pack_conv3
 
 
 class PlainUNetEngine(EngineBase):
-    def __init__(self, net, B, device):
+    def __init__(self, net, B, device, precision="bf16"):
         cfg = net.config
         H = cfg.data.image_size
-        super().__init__(device, B, H)
+        super().__init__(device, B, H, precision)
         self.net, self.cfg = net, cfg
         self.fixed_groups = 32
         d = cfg.data
@@ -75,8 +75,9 @@ class PlainUNetEngine(EngineBase):
         self.bias_table = None
 
         self.xin = torch.zeros((B, H, H, CIN_PAD), dtype=torch.bfloat16, device=dev)
+        self.xin_lo = torch.zeros_like(self.xin) if self.split else None
         self.eps = torch.zeros((B, spec["n_out"], H, H), dtype=torch.float32, device=dev)
-        x = Act(self.xin)
+        x = Act(self.xin, self.xin_lo)
         hs = []
         for j, s in enumerate(spec["down"]):
             p = f"downblocks.{j}"
@@ -108,6 +109,9 @@ class PlainUNetEngine(EngineBase):
                 up = self.new_act(x.H * 2, x.W * 2, x.C)
                 self._op(lambda li, a=x, o=up: ops.nearest_up2(a.t, o.t, a.B, a.H, a.W, a.C), "fir",
                          dict(bytes=x.t.numel() * 2 * 5))
+                if self.split:  # nearest-neighbour is a pure copy: replicate the residual plane too
+                    self._op(lambda li, a=x, o=up: ops.nearest_up2(a.lo, o.lo, a.B, a.H, a.W, a.C), "fir",
+                             dict(bytes=x.t.numel() * 2 * 5))
                 out = self.new_act(up.H, up.W, s["ch"], scratch=False)
                 self.gemm([(up, 9)], pack_conv3(sd[p + ".conv.weight"].to(dev)), out.t, EVC_OUT_BF16_ROWS, s["ch"],
                           bias=self.f32(p + ".conv.bias"), stats_of=out)
@@ -143,7 +147,7 @@ class PlainUNetEngine(EngineBase):
         b1 = sd[p + ".conv1.bias"].float()
         xs = [xa] + ([xb] if xb is not None else [])
         if (p + ".nin.weights") in sd:
-            w = torch.cat([w1, sd[p + ".nin.weights"].to(dev).to(torch.bfloat16)], dim=1).contiguous()
+            w = torch.cat([w1, sd[p + ".nin.weights"].to(dev).float()], dim=1).contiguous()
             bias = (b1 + sd[p + ".nin.bias"].float()).to(dev).contiguous()
             self._keep.append(bias)
             self.gemm([(a1, 9)] + [(x, 1) for x in xs], w, out.t, EVC_OUT_BF16_ROWS, cout, bias=bias, stats_of=out)
@@ -158,7 +162,7 @@ class PlainUNetEngine(EngineBase):
     def attn_block(self, p, s, x):
         """AttnBlock (unet.py:100-120): single head, scale 1/sqrt(C), x + OUT(h)."""
         sd, dev = self.sd, self.device
-        ws = [sd[p + f".{n}.weights"].to(dev).to(torch.bfloat16).contiguous() for n in ("Q", "K", "V", "OUT")]
+        ws = [sd[p + f".{n}.weights"].to(dev).float().contiguous() for n in ("Q", "K", "V", "OUT")]
         bs = [sd[p + f".{n}.bias"].float().to(dev).contiguous() for n in ("Q", "K", "V", "OUT")]
         return self.attn_core(x, self._gn_ss(p + ".normalize"), 1e-6, ws, bs, 1, 1.0)
 
@@ -184,6 +188,10 @@ class PlainUNetEngine(EngineBase):
         return self.bias_table
 
     def load_input(self, x, cond):
-        ops.pack_nchw(x.contiguous(), self.xin, 0)
+        ops.pack_nchw(x.contiguous(), self.xin, 0, dst_lo=self.xin_lo)
         if cond is not None:
-            ops.pack_nchw(cond.contiguous(), self.xin, self.c_x)
+            ops.pack_nchw(cond.contiguous(), self.xin, self.c_x, dst_lo=self.xin_lo)
+
+    def refresh_x(self, x):
+        if self.split:
+            ops.pack_nchw(x, self.xin, 0, dst_lo=self.xin_lo)

@@ -15,7 +15,8 @@ Behaviour kept from the reference (quirks included):
   * unknown keyword arguments are swallowed.
 Not supported (raise, no fallback): gamma noise, t_min > 0 (noised-start), frac_steps.
 Extra optional keywords: `noise` (sequence / tensor of per-step noise, used instead of the generator -- parity
-tests feed the oracle's noise through it) and `graph` (False = eager launches, default True).
+tests feed the oracle's noise through it), `graph` (False = eager launches, default True) and `precision`
+('bf16' default | 'fp32': split-bf16 x3 tensor-core arithmetic, per-step x_t within 1e-3 of the fp32 reference).
 """
 import numpy as np
 import torch
@@ -74,8 +75,10 @@ def _unsupported(gamma, t_min, frac_steps=None):
 
 
 def _ancestral(kind, x_mod, scorenet, cond, final_only, denoise, subsample_steps, clip_before, just_beta, same_noise,
-               noise_val, noise, graph):
+               noise_val, noise, graph, precision=None):
     net = _net_of(scorenet)
+    if precision is not None:
+        net.precision = precision
     steps, alphas, alphas_prev, betas = _subsampled_schedule(net, subsample_steps)
     L = len(steps)
     # per-step coefficients, evaluated with the same fp32 tensor expressions as the reference
@@ -113,27 +116,29 @@ def _ancestral(kind, x_mod, scorenet, cond, final_only, denoise, subsample_steps
 @torch.no_grad()
 def ddpm_sampler(x_mod, scorenet, cond=None, just_beta=False, final_only=False, denoise=True, subsample_steps=None,
                  same_noise=False, noise_val=None, frac_steps=None, verbose=False, log=False, clip_before=True,
-                 t_min=-1, gamma=False, noise=None, graph=True, **kwargs):
+                 t_min=-1, gamma=False, noise=None, graph=True, precision=None, **kwargs):
     """Ancestral DDPM sampling (reference models/__init__.py:207-342)."""
     _unsupported(gamma, t_min, frac_steps)
     return _ancestral("ddpm", x_mod, scorenet, cond, final_only, denoise, subsample_steps, clip_before, just_beta,
-                      same_noise, noise_val, noise, graph)
+                      same_noise, noise_val, noise, graph, precision)
 
 
 @torch.no_grad()
 def ddim_sampler(x_mod, scorenet, cond=None, final_only=False, denoise=True, subsample_steps=None, verbose=False,
-                 log=True, clip_before=True, t_min=-1, gamma=False, graph=True, **kwargs):
+                 log=True, clip_before=True, t_min=-1, gamma=False, graph=True, precision=None, **kwargs):
     """Deterministic DDIM sampling (reference models/__init__.py:103-204)."""
     _unsupported(gamma, t_min)
     return _ancestral("ddim", x_mod, scorenet, cond, final_only, denoise, subsample_steps, clip_before, False, False,
-                      None, None, graph)
+                      None, None, graph, precision)
 
 
 @torch.no_grad()
 def FPNDM_sampler(x_mod, scorenet, cond=None, final_only=False, denoise=True, subsample_steps=None, verbose=False,
-                  log=True, clip_before=True, t_min=-1, gamma=False, graph=True, **kwargs):
+                  log=True, clip_before=True, t_min=-1, gamma=False, graph=True, precision=None, **kwargs):
     """F-PNDM sampling: 3 Runge-Kutta steps then 4th-order Adams-Bashforth (reference models/__init__.py:39-100)."""
     net = _net_of(scorenet)
+    if precision is not None:
+        net.precision = precision
     alphas = net.alphas
     skip = len(alphas) // subsample_steps  # TypeError on None, like the reference (:62)
     steps = list(range(0, len(alphas), skip))

@@ -5,6 +5,8 @@ Only the configuration configs/mine.yml instantiates is supported (SURVEY.md sec
 positional embedding, BigGAN residual blocks with FIR resampling, GroupNorm/AdaGN, no SPADE, no 3-D variants,
 no cond_emb, no noise_in_cond, no gamma.  Anything else raises -- there is no fallback path.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -154,6 +156,8 @@ class NCSNpp(nn.Module):
                 mods.append(get_act_norm(s["ch"], None))
         self.all_modules = nn.ModuleList(mods)
         self._engines = {}
+        # 'bf16' (default, tensor-core speed) or 'fp32' (split-bf16 x3: per-step x_t within 1e-3 of the fp32 reference)
+        self.precision = os.environ.get("EVC_PRECISION", getattr(config, "precision", "bf16"))
 
     # -- engine management ------------------------------------------------------------------------
     def _weights_version(self):
@@ -167,12 +171,12 @@ class NCSNpp(nn.Module):
             raise EvcError("evcdiff runs on CUDA devices only; move the model with .to('cuda')")
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        key = (B, str(device))
+        key = (B, str(device), self.precision)
         ver = self._weights_version()
         hit = self._engines.get(key)
         if hit is None or hit[0] != ver:
             self._engines.pop(key, None)
-            hit = (ver, NCSNppEngine(self, B, device))
+            hit = (ver, NCSNppEngine(self, B, device, self.precision))
             self._engines[key] = hit
         return hit[1]
 
@@ -205,6 +209,15 @@ class UNetMore_DDPM(nn.Module):
         self.register_buffer("alphas_prev", torch.cat([self.alphas[1:], torch.tensor([1.0]).to(self.alphas)]))
         self.gamma = False
         self.noise_in_cond = False
+
+    @property
+    def precision(self):
+        """'bf16' (default) or 'fp32' (split-bf16 x3 tensor-core arithmetic, fp32-tolerance mode)."""
+        return self.unet.precision
+
+    @precision.setter
+    def precision(self, value):
+        self.unet.precision = value
 
     def engine(self, B, device=None):
         return self.unet.engine(B, device)

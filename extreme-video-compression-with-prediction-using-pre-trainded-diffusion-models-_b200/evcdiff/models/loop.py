@@ -121,6 +121,7 @@ class SamplerLoop:
                         self.noise.normal_()
                         nz = self.noise
                 ops.sampler_update(self.x, eng.eps, nz, self.x, eng.xin, c)
+                eng.refresh_x(self.x)
                 if not final_only:
                     images.append(self.x.to("cpu"))
 
@@ -180,19 +181,24 @@ class SamplerLoop:
                     ring.append(e1)
                     es = [ring[-1], ring[-2], ring[-3], ring[-4]]
                     ops.pndm_update(self.x, es, self.x, None, eng.xin, coef(t, tn, 4, (55.0, -59.0, 37.0, -9.0), 1 / 24))
+                    eng.refresh_x(self.x)
                 else:
                     tm = (t + tn) / 2
                     e2, e3, e4 = free[-1], free[-2], free[-3]
                     eng.forward(li[t]); e1.copy_(eng.eps)
                     ring.append(e1)
                     ops.pndm_update(self.x, [e1], self.scratch, None, eng.xin, coef(t, tm, 1, (1.0,), 1.0))
+                    eng.refresh_x(self.scratch)
                     eng.forward(li[tm]); e2.copy_(eng.eps)
                     ops.pndm_update(self.x, [e2], self.scratch, None, eng.xin, coef(t, tm, 1, (1.0,), 1.0))
+                    eng.refresh_x(self.scratch)
                     eng.forward(li[tm]); e3.copy_(eng.eps)
                     ops.pndm_update(self.x, [e3], self.scratch, None, eng.xin, coef(t, tn, 1, (1.0,), 1.0))
+                    eng.refresh_x(self.scratch)
                     eng.forward(li[tn]); e4.copy_(eng.eps)
                     ops.pndm_update(self.x, [e1, e2, e3, e4], self.x, None, eng.xin,
                                     coef(t, tn, 4, (1.0, 2.0, 2.0, 1.0), 1 / 6))
+                    eng.refresh_x(self.x)
                 if not final_only:
                     images.append(self.x.to("cpu"))
 

@@ -5,6 +5,8 @@ state-dict keys (reference models/unet.py:49-371; BASELINE config 5), evaluated 
 reference (unet.py:184).  UNet_SMLD is out of scope (SMLD samplers are not on the path)."""
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -145,6 +147,8 @@ class UNet(nn.Module):
         default_init(self.temb_dense[0], 1)
         default_init(self.temb_dense[2], 1)
         self._engines = {}
+        # 'bf16' (default, tensor-core speed) or 'fp32' (split-bf16 x3: per-step x_t within 1e-3 of the fp32 reference)
+        self.precision = os.environ.get("EVC_PRECISION", getattr(config, "precision", "bf16"))
 
     def _weights_version(self):
         return sum(p._version for p in self.parameters()) + 7919 * sum(p.data_ptr() % 65521 for p in self.parameters())
@@ -156,11 +160,11 @@ class UNet(nn.Module):
             raise EvcError("evcdiff runs on CUDA devices only; move the model with .to('cuda')")
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        key, ver = (B, str(device)), self._weights_version()
+        key, ver = (B, str(device), self.precision), self._weights_version()
         hit = self._engines.get(key)
         if hit is None or hit[0] != ver:
             self._engines.pop(key, None)
-            hit = (ver, PlainUNetEngine(self, B, device))
+            hit = (ver, PlainUNetEngine(self, B, device, self.precision))
             self._engines[key] = hit
         return hit[1]
 
@@ -197,6 +201,15 @@ class UNet_DDPM(nn.Module):
         self.register_buffer("alphas_prev", torch.cat([self.alphas[1:], torch.tensor([1.0]).to(self.alphas)]))
         self.gamma = False
         self.noise_in_cond = False
+
+    @property
+    def precision(self):
+        """'bf16' (default) or 'fp32' (split-bf16 x3 tensor-core arithmetic, fp32-tolerance mode)."""
+        return self.unet.precision
+
+    @precision.setter
+    def precision(self, value):
+        self.unet.precision = value
 
     def engine(self, B, device=None):
         return self.unet.engine(B, device)

@@ -28,7 +28,8 @@ class GemmPlan:
     """
 
     def __init__(self, segs, w, out, out_mode, out_ld, out_bs=0, bias=None, resid=None, resid_ld=0, alpha=1.0,
-                 bn=None, max_ctas=0, stats=None, stride=1, cta_group=None):
+                 bn=None, max_ctas=0, stats=None, stride=1, cta_group=None, segs_lo=None, w_lo=None, out_lo=None,
+                 resid_lo=None):
         lib = load()
         _require_cuda(w, out, bias, resid, *[s[0] for s in segs])
         d = GemmDesc()
@@ -78,7 +79,19 @@ class GemmPlan:
         if stats is not None:
             assert stats.dtype == torch.int64 and stats.is_cuda
             d.stats = stats.data_ptr()
-        self._keep = (segs, w, out, bias, resid, stats)
+        if w_lo is not None:  # split-precision operands: same shapes / strides as the hi planes
+            assert segs_lo is not None and len(segs_lo) == len(segs) and w_lo.shape == w.shape and w_lo.stride() == w.stride()
+            _require_cuda(w_lo, out_lo, resid_lo, *segs_lo)
+            for i, a in enumerate(segs_lo):
+                hi = segs[i][0]
+                assert a.dtype == torch.bfloat16 and a.shape == hi.shape and a.stride() == hi.stride()
+                d.a_lo[i].ptr = a.data_ptr()
+                d.a_lo[i].B, d.a_lo[i].H, d.a_lo[i].W, d.a_lo[i].C = a.shape
+                d.a_lo[i].stride_b, d.a_lo[i].stride_h, d.a_lo[i].stride_w = a.stride(0), a.stride(1), a.stride(2)
+            d.w_lo = w_lo.data_ptr()
+            d.out_lo = out_lo.data_ptr() if out_lo is not None else None
+            d.resid_lo = resid_lo.data_ptr() if resid_lo is not None else None
+        self._keep = (segs, w, out, bias, resid, stats, segs_lo, w_lo, out_lo, resid_lo)
         self._lib = lib
         h = C.c_void_p()
         check(lib.evc_gemm_plan_create(C.byref(d), C.byref(h)), "evc_gemm_plan_create")
@@ -182,25 +195,38 @@ def _default_workspace(device, nbytes):
     return ws
 
 
-def gn_stats(x, B, HW, C, stats, ldx=None, workspace=None):
+def gn_stats(x, B, HW, C, stats, ldx=None, workspace=None, x_lo=None):
     """stats (B,C,2) int64 (2^20 fixed point) = per-channel [sum, sumsq] of x (B*HW rows of C bf16).  workspace: zero-initialised
     uint8 scratch (shared between calls on one stream); a per-device default is used when omitted."""
-    _require_cuda(x, stats)
+    _require_cuda(x, stats, x_lo)
     if workspace is None:
         workspace = _default_workspace(x.device, gn_stats_workspace_bytes(B, HW, C))
-    check(load().evc_gn_stats(_ptr(x), ldx or C, B, HW, C, _ptr(stats), C, 0, _ptr(workspace), workspace.numel(),
-                              stream_ptr()), "evc_gn_stats")
+    if x_lo is None:
+        check(load().evc_gn_stats(_ptr(x), ldx or C, B, HW, C, _ptr(stats), C, 0, _ptr(workspace), workspace.numel(),
+                                  stream_ptr()), "evc_gn_stats")
+    else:
+        check(load().evc_gn_stats_split(_ptr(x), _ptr(x_lo), ldx or C, B, HW, C, _ptr(stats), C, 0, _ptr(workspace),
+                                        workspace.numel(), stream_ptr()), "evc_gn_stats_split")
 
 
-def gn_apply(x0, C0, x1, C1, B, HW, stats0, stats1, groups, eps, ss, adagn, silu, y):
-    _require_cuda(x0, x1, stats0, stats1, ss, y)
-    check(load().evc_gn_apply(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(stats0), _ptr(stats1), groups, eps, _ptr(ss),
-                              int(adagn), int(silu), _ptr(y), stream_ptr()), "evc_gn_apply")
+def gn_apply(x0, C0, x1, C1, B, HW, stats0, stats1, groups, eps, ss, adagn, silu, y, x0_lo=None, x1_lo=None, y_lo=None):
+    _require_cuda(x0, x1, stats0, stats1, ss, y, x0_lo, x1_lo, y_lo)
+    if y_lo is None:
+        check(load().evc_gn_apply(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(stats0), _ptr(stats1), groups, eps, _ptr(ss),
+                                  int(adagn), int(silu), _ptr(y), stream_ptr()), "evc_gn_apply")
+    else:
+        check(load().evc_gn_apply_split(_ptr(x0), _ptr(x0_lo), C0, _ptr(x1), _ptr(x1_lo), C1, B, HW, _ptr(stats0),
+                                        _ptr(stats1), groups, eps, _ptr(ss), int(adagn), int(silu), _ptr(y), _ptr(y_lo),
+                                        stream_ptr()), "evc_gn_apply_split")
 
 
-def fir_resample(x, y, B, H, W, C, up):
-    _require_cuda(x, y)
-    check(load().evc_fir_resample(_ptr(x), _ptr(y), B, H, W, C, int(up), stream_ptr()), "evc_fir_resample")
+def fir_resample(x, y, B, H, W, C, up, x_lo=None, y_lo=None):
+    _require_cuda(x, y, x_lo, y_lo)
+    if y_lo is None:
+        check(load().evc_fir_resample(_ptr(x), _ptr(y), B, H, W, C, int(up), stream_ptr()), "evc_fir_resample")
+    else:
+        check(load().evc_fir_resample_split(_ptr(x), _ptr(x_lo), _ptr(y), _ptr(y_lo), B, H, W, C, int(up), stream_ptr()),
+              "evc_fir_resample_split")
 
 
 def nearest_up2(x, y, B, H, W, C):
@@ -208,9 +234,12 @@ def nearest_up2(x, y, B, H, W, C):
     check(load().evc_nearest_up2(_ptr(x), _ptr(y), B, H, W, C, stream_ptr()), "evc_nearest_up2")
 
 
-def softmax_rows(S, P, rows, cols):
-    _require_cuda(S, P)
-    check(load().evc_softmax_rows(_ptr(S), _ptr(P), rows, cols, stream_ptr()), "evc_softmax_rows")
+def softmax_rows(S, P, rows, cols, P_lo=None):
+    _require_cuda(S, P, P_lo)
+    if P_lo is None:
+        check(load().evc_softmax_rows(_ptr(S), _ptr(P), rows, cols, stream_ptr()), "evc_softmax_rows")
+    else:
+        check(load().evc_softmax_rows_split(_ptr(S), _ptr(P), _ptr(P_lo), rows, cols, stream_ptr()), "evc_softmax_rows_split")
 
 
 def timestep_embedding(labels, freqs, dim, out):
@@ -228,13 +257,17 @@ def linear_f32(x, W, b, y, act_in=False, act_out=False):
           "evc_linear_f32")
 
 
-def pack_nchw(src, dst, c_off=0, scale=1.0, shift=0.0):
-    """src (B,C,H,W) fp32/fp64 contiguous -> channels [c_off, c_off+C) of dst (B,H,W,Cpad) bf16."""
-    _require_cuda(src, dst)
+def pack_nchw(src, dst, c_off=0, scale=1.0, shift=0.0, dst_lo=None):
+    """src (B,C,H,W) fp32/fp64 contiguous -> channels [c_off, c_off+C) of dst (B,H,W,Cpad) bf16 (+ residual plane)."""
+    _require_cuda(src, dst, dst_lo)
     assert src.is_contiguous() and dst.is_contiguous() and src.dtype in (torch.float32, torch.float64)
     B, Cc, H, W = src.shape
-    check(load().evc_pack_nchw(_ptr(src), int(src.dtype == torch.float64), B, Cc, H * W, scale, shift, _ptr(dst),
-                               dst.shape[-1], c_off, stream_ptr()), "evc_pack_nchw")
+    if dst_lo is None:
+        check(load().evc_pack_nchw(_ptr(src), int(src.dtype == torch.float64), B, Cc, H * W, scale, shift, _ptr(dst),
+                                   dst.shape[-1], c_off, stream_ptr()), "evc_pack_nchw")
+    else:
+        check(load().evc_pack_nchw_split(_ptr(src), int(src.dtype == torch.float64), B, Cc, H * W, scale, shift, _ptr(dst),
+                                         _ptr(dst_lo), dst.shape[-1], c_off, stream_ptr()), "evc_pack_nchw_split")
 
 
 def fill_zero(t):

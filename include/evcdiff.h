@@ -43,6 +43,10 @@ const char* evc_last_error(void);
 void evc_set_pdl(int enabled);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t evc_launch_count(void);
+/* sizeof() of the ABI structs as this library was compiled: 0 evc_tensor4, 1 evc_gemm_desc, 2 evc_attn_desc,
+ * 3 evc_step_coef, 4 evc_pndm_coef; -1 for an unknown id.  Bindings check their own struct layouts against it at
+ * load time (a shorter foreign struct would make the library read past its end). */
+int64_t evc_struct_size(int32_t which);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense contractions: implicit-GEMM convolution / batched GEMM on tcgen05 tensor cores.
@@ -101,6 +105,14 @@ typedef struct evc_gemm_desc {
   /* 0 = automatic, 1 = one CTA per 128-row tile, 2 = CTA pair (tcgen05 cta_group::2, 256-row tile; the pair shares
    * one B tile, each CTA staging half of it).  2 needs shared weights, bn % 32 == 0, bn >= 64, N % bn == 0. */
   int32_t cta_group;
+  /* Split-precision ("fp32-tolerance") operands, all NULL in the default bf16 mode.  Every bf16 tensor x is then a
+   * pair (hi, lo) with hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits); a product is accumulated as
+   * hi*hi + hi*lo + lo*hi in fp32.  a_lo[s] / w_lo / resid_lo have the layout of a[s] / w / resid; a bf16 output is
+   * written as the pair (out, out_lo).  Cost: 3x the MMA work and 2x the activation traffic. */
+  evc_tensor4 a_lo[3];
+  const void* w_lo;
+  void* out_lo;
+  const void* resid_lo;
 } evc_gemm_desc;
 
 typedef struct evc_gemm_plan evc_gemm_plan;
@@ -161,6 +173,19 @@ int evc_gn_stats(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, i
 int evc_gn_apply(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int32_t HW, const int64_t* stats0,
                  const int64_t* stats1, int32_t groups, float eps, const float* ss, int32_t adagn, int32_t silu,
                  void* y, evc_stream_t stream);
+
+/* Split-precision ("fp32-tolerance") variants: every bf16 tensor is a pair (x, x_lo) with value x + x_lo (see
+ * evc_gemm_desc.a_lo).  Same arithmetic in fp32, results written back as pairs. */
+int evc_gn_stats_split(const void* x, const void* x_lo, int64_t ldx, int32_t B, int32_t HW, int32_t C, int64_t* stats,
+                       int32_t c_total, int32_t c_off, void* workspace, int64_t workspace_bytes, evc_stream_t stream);
+int evc_gn_apply_split(const void* x0, const void* x0_lo, int32_t C0, const void* x1, const void* x1_lo, int32_t C1,
+                       int32_t B, int32_t HW, const int64_t* stats0, const int64_t* stats1, int32_t groups, float eps,
+                       const float* ss, int32_t adagn, int32_t silu, void* y, void* y_lo, evc_stream_t stream);
+int evc_fir_resample_split(const void* x, const void* x_lo, void* y, void* y_lo, int32_t B, int32_t H, int32_t W,
+                           int32_t C, int32_t up, evc_stream_t stream);
+int evc_softmax_rows_split(const float* S, void* P, void* P_lo, int64_t rows, int32_t cols, evc_stream_t stream);
+int evc_pack_nchw_split(const void* src, int32_t src_is_f64, int32_t B, int32_t C, int32_t HW, float scale, float shift,
+                        void* dst, void* dst_lo, int32_t Cpad, int32_t c_off, evc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * FIR [1,3,3,1] x2 resampling (upfirdn2d modes used by upsample_2d / downsample_2d,
