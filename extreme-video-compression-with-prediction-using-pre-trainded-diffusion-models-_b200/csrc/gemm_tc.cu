@@ -146,7 +146,7 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, const float (&f
   }
 }
 
-template <int CG>
+template <int CG, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_seg; ++s) tma_prefetch_desc(&p.a_map[p.seg_a[s]]);
     tma_prefetch_desc(&p.b_map[0]);
-    if (p.out_lo != nullptr) tma_prefetch_desc(&p.b_map[1]);
+    if (SPLIT) tma_prefetch_desc(&p.b_map[1]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (j < ncols && n + j < p.N) f[j] += __bfloat162float(r[j]);
-            if (p.resid_lo != nullptr) {
+            if (SPLIT && p.resid_lo != nullptr) {
               const __nv_bfloat16* r2 = p.resid_lo + pix * p.resid_ld + n;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
           store_chunk(p, f, ncols, n, pix, b, pin, p.out);
-          if (p.out_lo != nullptr) {
+          if (SPLIT && p.out_lo != nullptr) {
             float g[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) g[j] = f[j] - __bfloat162float(__float2bfloat16_rn(f[j]));
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           for (int j = 0; j < 32; ++j) {
             // bf16 mode: the value as stored; split mode: hi + lo represents f to 2^-17, use f itself
             const float r = (valid && j < ncols && n + j < p.N)
-                                ? (p.out_lo != nullptr ? f[j] : __bfloat162float(__float2bfloat16_rn(f[j])))
+                                ? ((SPLIT && p.out_lo != nullptr) ? f[j] : __bfloat162float(__float2bfloat16_rn(f[j])))
                                 : 0.f;
             f[j] = r;
             sq[j] = r * r;
@@ -470,6 +470,7 @@ struct evc_gemm_plan {
   int cg;  // 1: one CTA per 128-row tile; 2: CTA pair (cta_group::2), 256-row tile, B tile split across the pair
   int grid;
   int smem_bytes;
+  bool split;  // split-precision operands: the <CG, true> instantiation
   double flops;
 };
 
@@ -641,6 +642,7 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   }
   p.out = d->out;
   p.out_lo = d->out_lo;
+  pl->split = split;
   p.resid_lo = reinterpret_cast<const __nv_bfloat16*>(d->resid_lo);
   p.out_mode = d->out_mode;
   p.out_ld = d->out_ld;
@@ -688,19 +690,21 @@ extern "C" int evc_gemm_plan_launch(const evc_gemm_plan* pl, const float* bias_o
   if (pl == nullptr) return evc_set_error(EVC_ERR_INVALID, "null plan");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(evc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(evc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaSuccess;
+    void (*kernels[4])(GemmParams) = {evc_gemm_kernel<1, false>, evc_gemm_kernel<2, false>, evc_gemm_kernel<1, true>,
+                                      evc_gemm_kernel<2, true>};
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+      e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
     attr_set = true;
   }
   GemmParams p = pl->p;
   if (bias_override != nullptr) p.bias = bias_override;
   cudaError_t e;
-  if (pl->cg == 2)
-    e = evc_launch(evc_gemm_kernel<2>, dim3(pl->grid), dim3(kThreads), pl->smem_bytes, (cudaStream_t)stream, 2, p);
-  else
-    e = evc_launch(evc_gemm_kernel<1>, dim3(pl->grid), dim3(kThreads), pl->smem_bytes, (cudaStream_t)stream, 1, p);
+  const bool split = pl->split;
+  void (*kernel)(GemmParams) = pl->cg == 2 ? (split ? evc_gemm_kernel<2, true> : evc_gemm_kernel<2, false>)
+                                           : (split ? evc_gemm_kernel<1, true> : evc_gemm_kernel<1, false>);
+  e = evc_launch(kernel, dim3(pl->grid), dim3(kThreads), pl->smem_bytes, (cudaStream_t)stream, pl->cg, p);
   if (e != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
   return evc_check_launch(pl->cg == 2 ? "evc_gemm_kernel<2>" : "evc_gemm_kernel<1>");
 }
