@@ -2,41 +2,45 @@
 checkpoint's EMA dict with `load_state_dict` and copies it into the model with `ema` (city_sender.py:317-322).
 Pure parameter bookkeeping (no kernels); the engine notices the in-place `copy_` through the parameters'
 version counters and repacks its bf16 operands before the next sampling call."""
+import torch
 import torch.nn as nn
 
 
-def _unwrap(module):
-    return module.module if isinstance(module, nn.DataParallel) else module
+def _trainable(module):
+    """(name, parameter) pairs of the wrapped model, names without the DataParallel 'module.' prefix."""
+    inner = module.module if isinstance(module, nn.DataParallel) else module
+    return [(n, p) for n, p in inner.named_parameters() if p.requires_grad]
 
 
 class EMAHelper(object):
+    """shadow <- mu * shadow + (1 - mu) * param after every optimiser step; `ema()` writes the shadow into a model."""
+
     def __init__(self, mu=0.999):
         self.mu = mu
         self.shadow = {}
 
     def register(self, module):
-        for name, param in _unwrap(module).named_parameters():
-            if param.requires_grad:
-                self.shadow[name] = param.data.clone()
+        self.shadow.update({n: p.data.clone() for n, p in _trainable(module)})
 
+    @torch.no_grad()
     def update(self, module):
-        for name, param in _unwrap(module).named_parameters():
-            if param.requires_grad:
-                self.shadow[name].data = (1.0 - self.mu) * param.data + self.mu * self.shadow[name].data
+        keep = self.mu
+        for n, p in _trainable(module):
+            self.shadow[n] = keep * self.shadow[n] + (1.0 - keep) * p.data
 
+    @torch.no_grad()
     def ema(self, module):
-        for name, param in _unwrap(module).named_parameters():
-            if param.requires_grad:
-                param.data.copy_(self.shadow[name].data)
+        for n, p in _trainable(module):
+            p.data.copy_(self.shadow[n])  # in place: bumps the version counter the engine watches
 
     def ema_copy(self, module):
-        inner = _unwrap(module)
-        copy = type(inner)(inner.config).to(inner.config.device)
-        copy.load_state_dict(inner.state_dict())
-        if isinstance(module, nn.DataParallel):
-            copy = nn.DataParallel(copy)
-        self.ema(copy)
-        return copy
+        wrapped = isinstance(module, nn.DataParallel)
+        src = module.module if wrapped else module
+        twin = type(src)(src.config).to(src.config.device)
+        twin.load_state_dict(src.state_dict())
+        twin = nn.DataParallel(twin) if wrapped else twin
+        self.ema(twin)
+        return twin
 
     def state_dict(self):
         return self.shadow

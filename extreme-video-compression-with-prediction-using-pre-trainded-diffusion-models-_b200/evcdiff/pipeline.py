@@ -15,6 +15,31 @@ def shard_range(n_items, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def get_model(config, ckpt_file=None, states=None, kind="ncsnpp"):
+    """SenderCity.get_model (city_sender.py:304-324), done ONCE instead of once per sampling cycle: build the model,
+    load the checkpoint (`states[0]` = state dict whose keys may carry DataParallel's 'module.' prefix, `states[-1]` =
+    EMA shadow, used when config.model.ema), return the evaluation-mode model on config.device.  The bf16 operand
+    repack happens lazily at the first sampling call and again only if the parameters change."""
+    from .models.ema import EMAHelper
+    if kind == "ncsnpp":
+        from .models.better.ncsnpp_more import UNetMore_DDPM as Model
+    else:
+        from .models.unet import UNet_DDPM as Model
+    net = Model(config).to(config.device)
+    if states is None and ckpt_file is not None:
+        states = torch.load(ckpt_file, map_location=config.device)
+    if states is not None:
+        sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in states[0].items()}
+        net.load_state_dict(sd, strict=False)
+        if getattr(config.model, "ema", False):
+            helper = EMAHelper(mu=config.model.ema_rate)
+            helper.register(net)
+            helper.load_state_dict({(k[len("module."):] if k.startswith("module.") else k): v
+                                    for k, v in states[-1].items()})
+            helper.ema(net)
+    return net.eval()
+
+
 @torch.no_grad()
 def generate_frame(net, input_frames, config=None, sampler="DDPM", init_samples=None, to_host=True,
                    max_batch=64, **sampler_kwargs):

@@ -147,3 +147,18 @@ def test_checkpoint_loading_flow_like_city_sender():
     net = scorenet.module if hasattr(scorenet, "module") else scorenet
     assert all(bool((p == 0.25).all()) for p in net.parameters())
     assert net.unet._weights_version() != v0  # the engine will repack its operands
+
+
+def test_pipeline_get_model_loads_checkpoint_once():
+    """evcdiff.pipeline.get_model = city_sender.py:304-324 without the per-cycle reload."""
+    from evcdiff.models.better.ncsnpp_more import UNetMore_DDPM
+    from evcdiff.pipeline import get_model
+    cfg = common.tiny_config()
+    src = UNetMore_DDPM(cfg)
+    states = [{"module." + k: v.clone() for k, v in src.state_dict().items()}, "optimizer", 7,
+              {k: torch.full_like(p, -0.5) for k, p in src.named_parameters()}]
+    net = get_model(cfg, states=states)
+    assert not net.training and all(bool((p == -0.5).all()) for p in net.parameters())
+    cfg.model.ema = False
+    net = get_model(cfg, states=states)
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), src.state_dict().values()))
