@@ -1,6 +1,8 @@
 // HBM-bound kernels of the sampling path: GroupNorm statistics, fused normalise/AdaGN/SiLU, FIR x2
 // resampling, row softmax, layout packing.  All activations are NHWC bf16; every thread moves 16-byte
 // vectors (8 channels) so a warp touches whole 128-byte lines along the channel axis.
+#include <stdlib.h>
+
 #include "evc_host.h"
 #include "evc_ptx.cuh"
 
@@ -27,6 +29,34 @@ __device__ __forceinline__ float silu_f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
   return x * r;
+}
+// Two SiLUs with three MUFU ops: one reciprocal of the product (1+e0)(1+e1) serves both (t clamped at -40 so the
+// product stays finite; silu(-40) = -1.7e-16).
+__device__ __forceinline__ void silu_pair(float& x0, float& x1) {
+  float e0, e1, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaxf(x0, -40.f) * -1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaxf(x1, -40.f) * -1.4426950408889634f));
+  const float d0 = 1.f + e0, d1 = 1.f + e1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d0 * d1));
+  x0 *= r * d1;
+  x1 *= r * d0;
+}
+template <bool SILU, bool PAIR>
+__device__ __forceinline__ uint4 gn_affine_act(const uint4& raw, const float (&a)[8], const float (&bb)[8]) {
+  float f[8];
+  unpack8(raw, f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], a[j], bb[j]);
+  if (SILU) {
+    if (PAIR) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) silu_pair(f[j], f[j + 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+    }
+  }
+  return pack8(f);
 }
 // split-precision pair (hi, lo) <-> fp32: x = hi + lo, hi = bf16(x), lo = bf16(x - hi)
 __device__ __forceinline__ void split8(const float (&f)[8], uint4& hi, uint4& lo) {
@@ -168,7 +198,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
                                                        const __nv_bfloat16* __restrict__ x1_lo,
                                                        __nv_bfloat16* __restrict__ y_lo) {
   __shared__ float s_mean[64], s_rstd[64];
-  __shared__ float s_ps[64][9], s_pq[64][9];
+  __shared__ float2 s_ch[2048];  // per-channel (sum, sum of squares)
   pdl_wait();
   pdl_trigger();
   const int C = C0 + C1;
@@ -176,45 +206,8 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
   const int cpg = C / groups;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int nthr = blockDim.x * blockDim.y;
-  const float inv_n = 1.f / ((float)cpg * (float)HW);
-  // group statistics from the per-channel sums: `per` threads per group, partials combined in a fixed order
-  int per = nthr / groups;
-  per = per < 1 ? 1 : (per > 8 ? 8 : per);
-  for (int t = tid; t < groups * per; t += nthr) {
-    const int g = t / per, k = t % per;
-    float s = 0.f, q = 0.f;
-    for (int j = k; j < cpg; j += per) {
-      const int cc = g * cpg + j;
-      const long long* st = (cc < C0) ? stats0 + ((long long)b * C0 + cc) * 2 : stats1 + ((long long)b * C1 + (cc - C0)) * 2;
-      s += (float)((double)st[0] * (1.0 / 1048576.0));
-      q += (float)((double)st[1] * (1.0 / 1048576.0));
-    }
-    s_ps[g][k] = s;
-    s_pq[g][k] = q;
-  }
-  __syncthreads();
-  for (int g = tid; g < groups; g += nthr) {
-    float s = 0.f, q = 0.f;
-    for (int k = 0; k < per; ++k) {
-      s += s_ps[g][k];
-      q += s_pq[g][k];
-    }
-    const float mean = s * inv_n;
-    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-    s_mean[g] = mean;
-    s_rstd[g] = rsqrtf(var + eps);
-  }
-  __syncthreads();
   const int v = threadIdx.x;  // channel vector
   const int c = v * 8;
-  float a[8], bb[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (c + j) / cpg;
-    const float gam = adagn ? (1.f + ss[c + j]) : ss[c + j];
-    a[j] = s_rstd[g] * gam;
-    bb[j] = ss[C + c + j] - s_mean[g] * a[j];
-  }
   const bool first = (c < C0);
   const int ld = first ? C0 : C1;
   const int rows = blockDim.y;
@@ -223,11 +216,55 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
   const int p0 = p_begin + threadIdx.y;
   const __nv_bfloat16* src = (first ? x0 + c : x1 + (c - C0)) + ((long long)b * HW + p0) * ld;
   __nv_bfloat16* dst = y + ((long long)b * HW + p0) * C + c;
-  if (y_lo != nullptr) {
+  const long long sstep = (long long)rows * ld, dstep = (long long)rows * C;
+  int n = (p0 < p_end) ? (p_end - p0 + rows - 1) / rows : 0;  // pixels this thread handles
+  const bool split = (y_lo != nullptr);
+  // the first four pixel loads go out before the statistics are touched: their latency hides the prologue
+  uint4 cur[4];
+  if (!split && n >= 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cur[k] = ld_nc16(src + k * sstep);
+  }
+  // prologue, one global round trip: per-channel sums -> shared; the (scale, shift) rows are fetched meanwhile
+  for (int cc = tid; cc < C; cc += nthr) {
+    const longlong2 st = *reinterpret_cast<const longlong2*>(
+        (cc < C0) ? stats0 + ((long long)b * C0 + cc) * 2 : stats1 + ((long long)b * C1 + (cc - C0)) * 2);
+    s_ch[cc] = make_float2((float)((double)st.x * (1.0 / 1048576.0)), (float)((double)st.y * (1.0 / 1048576.0)));
+  }
+  float gam[8], bet[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(ss + c), g1 = *reinterpret_cast<const float4*>(ss + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(ss + C + c), b1 = *reinterpret_cast<const float4*>(ss + C + c + 4);
+    gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
+    bet[0] = b0.x; bet[1] = b0.y; bet[2] = b0.z; bet[3] = b0.w; bet[4] = b1.x; bet[5] = b1.y; bet[6] = b1.z; bet[7] = b1.w;
+  }
+  __syncthreads();
+  // group statistics: one thread per group, channels summed in index order (deterministic)
+  if (tid < groups) {
+    float s = 0.f, q = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      const float2 t = s_ch[tid * cpg + j];
+      s += t.x;
+      q += t.y;
+    }
+    const float inv_n = 1.f / ((float)cpg * (float)HW);
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    s_mean[tid] = mean;
+    s_rstd[tid] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  float a[8], bb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    a[j] = s_rstd[g] * (adagn ? (1.f + gam[j]) : gam[j]);
+    bb[j] = bet[j] - s_mean[g] * a[j];
+  }
+  if (split) {
     // split-precision path (accuracy mode, not tuned): x = hi + lo in, (hi, lo) out
     const __nv_bfloat16* src_lo = (first ? x0_lo + c : x1_lo + (c - C0)) + ((long long)b * HW + p0) * ld;
     __nv_bfloat16* dst_lo = y_lo + ((long long)b * HW + p0) * C + c;
-    const long long ss1 = (long long)rows * ld, ds1 = (long long)rows * C;
     for (int p = p0; p < p_end; p += rows) {
       float f[8];
       unpack8(ld_nc16(src), f);
@@ -241,18 +278,11 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
       split8(f, hi, lo);
       *reinterpret_cast<uint4*>(dst) = hi;
       *reinterpret_cast<uint4*>(dst_lo) = lo;
-      src += ss1; src_lo += ss1; dst += ds1; dst_lo += ds1;
+      src += sstep; src_lo += sstep; dst += dstep; dst_lo += dstep;
     }
     return;
   }
-  const long long sstep = (long long)rows * ld, dstep = (long long)rows * C;
-  int n = (p0 < p_end) ? (p_end - p0 + rows - 1) / rows : 0;  // pixels this thread handles
   // software pipeline: the loads of the next four pixels are in flight while the current four are normalised
-  uint4 cur[4];
-  if (n >= 4) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cur[k] = ld_nc16(src + k * sstep);
-  }
   while (n >= 4) {
     uint4 nxt[4];
     const bool more = (n >= 8);
@@ -261,16 +291,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
       for (int k = 0; k < 4; ++k) nxt[k] = ld_nc16(src + (4 + k) * sstep);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float f[8];
-      unpack8(cur[k], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float t = fmaf(f[j], a[j], bb[j]);
-        f[j] = SILU ? silu_f(t) : t;
-      }
-      *reinterpret_cast<uint4*>(dst + k * dstep) = pack8(f);
-    }
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dst + k * dstep) = gn_affine_act<SILU, true>(cur[k], a, bb);
     src += 4 * sstep;
     dst += 4 * dstep;
     n -= 4;
@@ -280,14 +301,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
     }
   }
   for (; n > 0; --n) {
-    float f[8];
-    unpack8(ld_nc16(src), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float t = fmaf(f[j], a[j], bb[j]);
-      f[j] = SILU ? silu_f(t) : t;
-    }
-    *reinterpret_cast<uint4*>(dst) = pack8(f);
+    *reinterpret_cast<uint4*>(dst) = gn_affine_act<SILU, true>(ld_nc16(src), a, bb);
     src += sstep;
     dst += dstep;
   }
@@ -606,14 +620,30 @@ static int gn_apply_impl(const void* x0, const void* x0_lo, int32_t C0, const vo
   const int C = C0 + C1;
   const int nvec = C / 8;
   if (nvec > 256 || groups > 64) return evc_set_error(EVC_ERR_INVALID, "evc_gn_apply: C > 2048 or groups > 64");
+  if ((reinterpret_cast<uintptr_t>(stats0) & 15) || (reinterpret_cast<uintptr_t>(stats1) & 15) ||
+      (reinterpret_cast<uintptr_t>(ss) & 15))
+    return evc_set_error(EVC_ERR_INVALID, "evc_gn_apply: stats / ss must be 16-byte aligned");
   int rows = 256 / nvec;
   if (rows < 1) rows = 1;
   const int sms = evc_num_sms();
+  static int waves = -1;
+  if (waves < 0) {
+    const char* e = getenv("EVC_GN_WAVES");
+    waves = e ? atoi(e) : 1;
+  }
   int chunks = (sms * 6 + B - 1) / B;
+  if (waves > 0) {
+    // whole waves of resident blocks (3 per SM, __launch_bounds__): B * chunks just below waves * 3 * sms
+    chunks = (sms * 3 * waves) / B;
+  }
   const int max_chunks = (HW + rows - 1) / rows;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
-  const int ppb = (HW + chunks - 1) / chunks;
+  int ppb = (HW + chunks - 1) / chunks;
+  if (waves > 0) {
+    // the rounding of pixels-per-block may only lower the number of blocks
+    while (ppb > 1 && (long long)((HW + ppb - 2) / (ppb - 1)) * B <= (long long)sms * 3 * waves) --ppb;
+  }
   chunks = (HW + ppb - 1) / ppb;
   dim3 grid(chunks, B), block(nvec, rows);
   cudaError_t le = evc_launch(silu ? gn_apply_kernel<true> : gn_apply_kernel<false>, grid, block, 0, (cudaStream_t)stream, 1,
