@@ -33,10 +33,6 @@ struct alignas(64) AttnParams {
   long long out_ld;    // elements between consecutive query rows
 };
 
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
 __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;

@@ -10,6 +10,8 @@
 //     loop of tile i+1.
 // Replaces cuDNN conv2d / cuBLAS einsum of the reference (models/better/layers.py:89-113, 521-544;
 // models/better/layerspp.py:239-243; models/unet.py:49-63, 114-119).
+#include <stdlib.h>
+
 #include "evc_host.h"
 #include "evc_ptx.cuh"
 
@@ -24,12 +26,30 @@ constexpr int kAccStride = 256;  // TMEM columns between the two accumulator sta
 
 constexpr int kMaxVSeg = 9;
 
+#ifdef EVC_GEMM_PROF
+// Wait-time probe (tools/gpu_gemm_waits.py; never compiled into the shipped library):
+// [0] MMA warp total, [1] MMA waits on full (operands), [2] MMA waits on tempty (accumulator),
+// [3] producer total, [4] producer waits on empty, [5] epilogue total, [6] epilogue waits on tfull, [7] CTAs
+__device__ unsigned long long g_prof[16];  // [8] epilogue: prefetch + bar.sync, [9] tcgen05.ld + wait, [10] math + stores + stats
+#define PROF_DECL(...) __VA_ARGS__
+#define PROF_T0(v) const long long v = clock64()
+#define PROF_ADD(acc, v) acc += clock64() - v
+#define PROF_OUT(i, acc) atomicAdd(&g_prof[i], (unsigned long long)(acc))
+#else
+#define PROF_DECL(...)
+#define PROF_T0(v)
+#define PROF_ADD(acc, v)
+#define PROF_OUT(i, acc)
+#endif
+
 // Split-precision ("fp32-tolerance") mode: every bf16 tensor has a second bf16 plane holding the rounding residual
 // (x = hi + lo carries 16 mantissa bits) and a product is evaluated as hi*hi + hi*lo + lo*hi in the fp32 accumulator.
 // In the K loop this is simply three "virtual segments" per source segment: (A_hi, W_hi), (A_hi, W_lo), (A_lo, W_hi).
 struct alignas(64) GemmParams {
   CUtensorMap a_map[6];  // [0,3) hi planes of the source segments, [3,6) lo planes
   CUtensorMap b_map[2];  // W hi, W lo
+  CUtensorMap out_map;   // bf16 row output as a 2-D tensor (N, B*H*W), 32 x 32 boxes, 64 B swizzle (TMA-store epilogue)
+  int tma_out;           // 0: per-thread global stores; 1 / 2: TMA stores through 1 / 2 staging buffers per warp
   int n_seg;             // number of virtual segments
   int seg_a[kMaxVSeg];   // a_map index
   int seg_b[kMaxVSeg];   // b_map index
@@ -201,6 +221,8 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
+    PROF_DECL(long long w_empty = 0;)
+    PROF_T0(t_prod);
     for (int tile = unit; tile < total_tiles; tile += num_units) {
       int x0, y0, b0, n0;
       decode_tile<CG>(p, tile, rank, x0, y0, b0, n0);
@@ -215,7 +237,9 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           const int dy = (taps == 9) ? (t / 3 - 1) : 0;
           const int dx = (taps == 9) ? (t % 3 - 1) : 0;
           for (int c = 0; c < p.seg_kb[s]; ++c) {
+            PROF_T0(t_e);
             mbar_wait(empty_bar(stage), phase ^ 1u);
+            PROF_ADD(w_empty, t_e);
             const uint32_t sa = base + stage * stage_bytes;
             if (CG == 2) {
               // both CTAs' bytes land on the leader's barrier; the peer contributes a plain (remote) arrival
@@ -236,20 +260,30 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         }
       }
     }
+    PROF_DECL(long long tot_prod = 0;)
+    PROF_ADD(tot_prod, t_prod);
+    PROF_OUT(3, tot_prod);
+    PROF_OUT(4, w_empty);
   } else if (warp == 1 && lane == 0 && rank == 0) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     const uint32_t idesc = umma_idesc_bf16(128u * CG, static_cast<uint32_t>(p.BN));
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    PROF_DECL(long long w_full = 0; long long w_tempty = 0;)
+    PROF_T0(t_mma);
     for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
+      PROF_T0(t_te);
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      PROF_ADD(w_tempty, t_te);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * kAccStride;
       for (int kb = 0; kb < p.total_kb; ++kb) {
+        PROF_T0(t_f);
         mbar_wait(full_bar(stage), phase);
+        PROF_ADD(w_full, t_f);
         tc_fence_after();
         const uint32_t sa = base + stage * stage_bytes;
         const uint64_t da = umma_desc_sw128(sa);
@@ -273,6 +307,12 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         }
       }
     }
+    PROF_DECL(long long tot_mma = 0;)
+    PROF_ADD(tot_mma, t_mma);
+    PROF_OUT(0, tot_mma);
+    PROF_OUT(1, w_full);
+    PROF_OUT(2, w_tempty);
+    PROF_OUT(7, 1);
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     // Per tile: (1) while the main loop of this tile is still running, stage the bias slice in smem and
@@ -293,7 +333,16 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     const uint32_t sres_u32 = bar_base + 256u + 1024u + static_cast<uint32_t>(row) * res_pitch;
     // [4 warps][BN][2] floats, after the residual rows
     float* sstat = reinterpret_cast<float*>(gsm + (bar_base - base) + 256 + 1024 + (p.resid_smem ? 128u * res_pitch : 0u));
+    // TMA-store staging: [8 warps][tma_out buffers][32 rows x 64 B], 64 B swizzle, after the statistics scratch
+    const uint32_t stg_off = (bar_base - base) + 256u + 1024u + (p.resid_smem ? 128u * res_pitch : 0u) +
+                             (p.stats != nullptr ? 32u * static_cast<uint32_t>(p.BN) : 0u);
+    const uint32_t stg_al = (stg_off + 1023u) & ~1023u;
+    uint8_t* stg_base = gsm + stg_al + static_cast<uint32_t>(warp - 4) * static_cast<uint32_t>(p.tma_out) * 2048u;
+    const uint32_t stg_base_u32 = base + stg_al + static_cast<uint32_t>(warp - 4) * static_cast<uint32_t>(p.tma_out) * 2048u;
+    int stg_i = 0;
     int it = 0;
+    PROF_DECL(long long w_tfull = 0; long long w_pre = 0; long long w_ld = 0; long long w_rest = 0;)
+    PROF_T0(t_epi);
     for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
@@ -306,6 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       const bool full_n = (n0 + p.BN <= p.N);
       const bool resid_fast = (p.resid != nullptr) && p.resid_smem && full_n;
       // (1) prefetch
+      PROF_T0(t_pre);
       asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone is done with the previous tile's sbias
       if (p.bias != nullptr) {
         for (int j = e; j < p.BN; j += kEpiThreads) sbias[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
@@ -320,8 +370,11 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");  // sbias visible
+      PROF_ADD(w_pre, t_pre);
       // (2) accumulator ready
+      PROF_T0(t_tf);
       mbar_wait(tfull_bar(acc), acc_phase);
+      PROF_ADD(w_tfull, t_tf);
       tc_fence_after();
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
@@ -329,11 +382,14 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
         const int ncols = min(32, p.BN - c0);
         uint32_t v[32];
+        PROF_T0(t_ld);
         if (ncols == 32)
           tmem_ld_32x32(taddr + c0, v);
         else
           tmem_ld_32x16(taddr + c0, v);
         tmem_ld_wait();
+        PROF_ADD(w_ld, t_ld);
+        PROF_T0(t_rest);
         if (c0 + 64 >= p.BN) {
           released = true;
           // last TMEM read of this tile is complete: hand the accumulator stage back to the MMA warp
@@ -348,6 +404,106 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = (j < ncols) ? __uint_as_float(v[j]) : 0.f;
+        if (!SPLIT && p.tma_out != 0) {
+          // ---- staged path (bf16 rows, full 128-row tiles, BN % 32 == 0): +bias +residual, *alpha -> swizzled smem
+          // -> one TMA store per 32 x 32 chunk; rows / columns outside the tensor are clipped by the TMA unit.
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(sbias + c0 + j);
+              f[j + 0] += bv.x;
+              f[j + 1] += bv.y;
+              f[j + 2] += bv.z;
+              f[j + 3] += bv.w;
+            }
+          }
+          if (resid_fast) {
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 u = *reinterpret_cast<const uint4*>(sres + (c0 + j) * 2);
+                f[j + 0] += bf16_lo(u.x);
+                f[j + 1] += bf16_hi(u.x);
+                f[j + 2] += bf16_lo(u.y);
+                f[j + 3] += bf16_hi(u.y);
+                f[j + 4] += bf16_lo(u.z);
+                f[j + 5] += bf16_hi(u.z);
+                f[j + 6] += bf16_lo(u.w);
+                f[j + 7] += bf16_hi(u.w);
+              }
+            }
+          } else if (p.resid != nullptr && valid) {
+            const __nv_bfloat16* r = p.resid + pix * p.resid_ld + n;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) f[j] += __bfloat162float(r[j]);
+          }
+          const uint32_t boff = (p.tma_out == 2 ? static_cast<uint32_t>(stg_i & 1) : 0u) * 2048u;
+          ++stg_i;
+          if (lane == 0) {  // the TMA unit must have finished reading this buffer (store issued two / one chunks ago)
+            if (p.tma_out == 2) bulk_wait_read<1>();
+            else bulk_wait_read<0>();
+          }
+          __syncwarp();
+          uint8_t* srow = stg_base + boff + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(f[8 * j + 0] * p.alpha, f[8 * j + 1] * p.alpha);
+            u.y = pack_bf16x2(f[8 * j + 2] * p.alpha, f[8 * j + 3] * p.alpha);
+            u.z = pack_bf16x2(f[8 * j + 4] * p.alpha, f[8 * j + 5] * p.alpha);
+            u.w = pack_bf16x2(f[8 * j + 6] * p.alpha, f[8 * j + 7] * p.alpha);
+            *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = u;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const long long tile_pix = ((long long)b0 * p.H + y0) * p.W + x0;  // tile rows are consecutive pixels
+            tma_store_2d(&p.out_map, stg_base_u32 + boff, n, static_cast<int>(tile_pix) + q * 32);
+            bulk_commit();
+          }
+          if (p.stats != nullptr) {
+            // column sums of the values as stored, read back from the staging buffer: lane -> (row parity, column
+            // pair); 16 conflict-free 4-byte loads per lane, then one exchange between the two parities
+            const int cp = lane & 15, par = lane >> 4;
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            const uint8_t* sb = stg_base + boff + ((cp & 3) << 2);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const int rr = 2 * r + par;
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(sb + rr * 64 + (((cp >> 2) ^ (r & 3)) << 4));
+              const float a0 = bf16_lo(u), a1 = bf16_hi(u);
+              s0 += a0;
+              s1 += a1;
+              q0 = fmaf(a0, a0, q0);
+              q1 = fmaf(a1, a1, q1);
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+            q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+            const int col = c0 + 2 * cp;
+            if (p.stats_combine) {
+              if (lane < 16) *reinterpret_cast<float4*>(sstat + (q * p.BN + col) * 2) = make_float4(s0, q0, s1, q1);
+            } else {
+              const int bw = b0 + (q * 32) / p.sample_rows;  // all 32 rows of this warp belong to one sample
+              if (bw < p.B && lane < 16) {
+                long long* dst = p.stats + ((long long)bw * p.N + n0 + col) * 2;
+                if (n0 + col < p.N) {
+                  stat_add(dst, s0);
+                  stat_add(dst + 1, q0);
+                }
+                if (n0 + col + 1 < p.N) {
+                  stat_add(dst + 2, s1);
+                  stat_add(dst + 3, q1);
+                }
+              }
+            }
+          }
+          PROF_ADD(w_rest, t_rest);
+          continue;
+        }
         if (valid) {
           if (p.bias != nullptr) {
 #pragma unroll
@@ -426,6 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
             }
           }
         }
+        PROF_ADD(w_rest, t_rest);
       }
       if (!released) {  // this warp had no chunk in this tile (BN <= 32 and grp == 1)
         tc_fence_before();
@@ -448,6 +605,18 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         }
       }
     }
+    if (p.tma_out != 0 && lane == 0) bulk_wait_all();  // staging buffers are read before the CTA's smem goes away
+#ifdef EVC_GEMM_PROF
+    if (e == 0 && rank == 0) {
+      long long tot_epi = 0;
+      PROF_ADD(tot_epi, t_epi);
+      PROF_OUT(5, tot_epi);
+      PROF_OUT(6, w_tfull);
+      PROF_OUT(8, w_pre);
+      PROF_OUT(9, w_ld);
+      PROF_OUT(10, w_rest);
+    }
+#endif
   }
 
   tc_fence_before();
@@ -475,13 +644,13 @@ struct evc_gemm_plan {
 };
 
 static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, int conv_stride = 1) {
+                      const uint32_t* box, int conv_stride = 1, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = evc_get_encode_tiled();
   if (enc == nullptr) return evc_set_error(EVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   uint32_t estr[5] = {1, 1, 1, 1, 1};
   if (rank == 4) estr[1] = estr[2] = (uint32_t)conv_stride;  // W and H traversal stride of a strided convolution
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -665,7 +834,30 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     delete pl;
     return evc_set_error(EVC_ERR_INVALID, "fused GroupNorm statistics need bf16 row output and H*W % 32 == 0");
   }
-  const int tail_bytes = 256 + 1024 + (p.resid_smem ? 128 * (d->bn * 2 + 16) : 0) + (d->stats ? 32 * d->bn : 0);
+  int tail_bytes = 256 + 1024 + (p.resid_smem ? 128 * (d->bn * 2 + 16) : 0) + (d->stats ? 32 * d->bn : 0);
+  // TMA-store epilogue (see the kernel): bf16 rows, whole 128-row tiles, 32-column chunks
+  static int tma_env = -1;
+  if (tma_env < 0) {
+    const char* e = getenv("EVC_GEMM_TMA_STORE");
+    tma_env = e ? atoi(e) : 2;
+  }
+  p.tma_out = 0;
+  const long long m_total = (long long)d->B * d->H * d->W;
+  if (tma_env > 0 && !split && d->out_mode == EVC_OUT_BF16_ROWS && p.rows_valid == 128 && (d->bn % 32) == 0 &&
+      (d->out_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 && m_total < (1ll << 31)) {
+    uint64_t dims[2] = {(uint64_t)d->w_rows, (uint64_t)m_total};
+    uint64_t strides[1] = {(uint64_t)d->out_ld * 2};
+    uint32_t box[2] = {32, 32};
+    int rc = encode_map(&p.out_map, d->out, 2, dims, strides, box, 1, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != EVC_OK) {
+      delete pl;
+      return rc;
+    }
+    // two staging buffers per epilogue warp unless that would leave fewer than four pipeline stages
+    const int tail2 = tail_bytes + 1024 + 8 * 2 * 2048;
+    p.tma_out = (tma_env >= 2 && (227 * 1024 - 1024 - tail2) / stage_bytes >= 4) ? 2 : 1;
+    tail_bytes += 1024 + 8 * p.tma_out * 2048;
+  }
   const int budget = 227 * 1024 - 1024 /*align slack*/ - tail_bytes;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -713,3 +905,14 @@ extern "C" int evc_gemm_plan_cta_group(const evc_gemm_plan* pl) { return pl ? pl
 
 extern "C" void evc_gemm_plan_destroy(evc_gemm_plan* pl) { delete pl; }
 extern "C" double evc_gemm_plan_flops(const evc_gemm_plan* pl) { return pl ? pl->flops : 0.0; }
+
+#ifdef EVC_GEMM_PROF
+// debug build only: copies the wait-time counters to the host and clears them
+extern "C" int evc_gemm_prof_read(unsigned long long* host8) {
+  cudaError_t e = cudaMemcpyFromSymbol(host8, evc::g_prof, sizeof(unsigned long long) * 16);
+  if (e != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
+  unsigned long long z[16] = {0};
+  e = cudaMemcpyToSymbol(evc::g_prof, z, sizeof(z));
+  return e == cudaSuccess ? EVC_OK : evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
+}
+#endif

@@ -1,0 +1,58 @@
+"""Where do the GEMM kernel's warps wait?  Needs a library built with -DEVC_GEMM_PROF (tools/build_prof.sh).
+Prints, per conv shape of the 128x128 / 64x64 levels at B=46, the share of the MMA-issuing thread's time spent
+waiting for operands (TMA -> `full`) and for a free accumulator (epilogue -> `tempty`)."""
+import ctypes as C
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "extreme-video-compression-with-prediction-using-pre-trainded-diffusion-models-_b200")]
+import torch
+from evcdiff import ops, _lib
+
+lib = _lib.load()
+lib.evc_gemm_prof_read.argtypes = [C.POINTER(C.c_uint64)]
+DEV = "cuda"
+B = int(os.environ.get("B", "46"))
+
+
+def run(name, H, Cins, N, taps=9, resid=False, stats=False, cg=None, reps=5):
+    segs = [(torch.randn(B, H, H, c, device=DEV).to(torch.bfloat16), taps) for c in Cins]
+    K = sum(taps * c for c in Cins)
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).to(torch.bfloat16)
+    out = torch.empty(B, H, H, N, device=DEV, dtype=torch.bfloat16)
+    r = torch.randn(B, H, H, N, device=DEV).to(torch.bfloat16) if resid else None
+    st = torch.zeros(B, N, 2, device=DEV, dtype=torch.int64) if stats else None
+    plan = ops.GemmPlan(segs, w, out, 0, out_ld=N, bias=torch.zeros(N, device=DEV), resid=r, resid_ld=N if resid else 0,
+                        alpha=1.0, stats=st, cta_group=cg)
+    for _ in range(2):
+        plan.launch()
+    torch.cuda.synchronize()
+    buf = (C.c_uint64 * 16)()
+    lib.evc_gemm_prof_read(buf)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        plan.launch()
+    e1.record()
+    torch.cuda.synchronize()
+    lib.evc_gemm_prof_read(buf)
+    v = [float(x) for x in buf]
+    ms = e0.elapsed_time(e1) / reps
+    tf = plan.flops / ms / 1e9
+    print(f"{name:34s} cg={plan.cta_group} {ms:7.3f} ms {tf:7.1f} TF | MMA thread: operands-wait {100 * v[1] / v[0]:5.1f}% "
+          f"accumulator-wait {100 * v[2] / v[0]:5.1f}% issue {100 * (v[0] - v[1] - v[2]) / v[0]:5.1f}% | producer waits for a free "
+          f"stage {100 * v[4] / v[3]:5.1f}% | epilogue: waits for the accumulator {100 * v[6] / v[5]:5.1f}%, prefetch+bar.sync "
+          f"{100 * v[8] / v[5]:5.1f}%, tcgen05.ld {100 * v[9] / v[5]:5.1f}%, math+stores+stats {100 * v[10] / v[5]:5.1f}%", flush=True)
+
+
+run("128^2 192->192", 128, [192], 192)
+run("128^2 192->192 +stats", 128, [192], 192, stats=True)
+run("128^2 192->192 +resid", 128, [192], 192, resid=True)
+run("128^2 192->192 +stats cg1", 128, [192], 192, stats=True, cg=1)
+run("128^2 384->192 +stats", 128, [192, 192], 192, stats=True)
+run("128^2 192->192 + 1x1 skip", 128, [192], 192, resid=True)
+run("64^2 192->192 +stats", 64, [192], 192, stats=True)
+run("64^2 384->384 +stats", 64, [384], 384, stats=True)
+run("32^2 384->384 +stats", 32, [384], 384, stats=True)
+run("32^2 NIN 384->384 1x1", 32, [384], 384, taps=1)
+run("16^2 576->576 +stats", 16, [576], 576, stats=True)
+run("8^2 768->768 +stats", 8, [768], 768, stats=True)
