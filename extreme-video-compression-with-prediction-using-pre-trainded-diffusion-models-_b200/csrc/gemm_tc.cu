@@ -50,6 +50,12 @@ struct alignas(64) GemmParams {
   CUtensorMap b_map[2];  // W hi, W lo
   CUtensorMap out_map;   // bf16 row output as a 2-D tensor (N, B*H*W), 32 x 32 boxes, 64 B swizzle (TMA-store epilogue)
   int tma_out;           // 0: per-thread global stores; 1 / 2: TMA stores through 1 / 2 staging buffers per warp
+  CUtensorMap resid_map; // residual as a 2-D tensor (N, B*H*W), 64 x 128 boxes, 128 B swizzle
+  int resid_tma;         // 1: the tile's residual rows are fetched by TMA (needs tma_out), 0: cp.async per thread
+  int off_resid, off_stat, off_stage;  // byte offsets of the epilogue scratch areas behind the barrier block
+#ifdef EVC_GEMM_PROF
+  int exp_alt;           // timing experiment (wrong results): alternate the accumulator between consecutive MMAs
+#endif
   int n_seg;             // number of virtual segments
   int seg_a[kMaxVSeg];   // a_map index
   int seg_b[kMaxVSeg];   // b_map index
@@ -184,6 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
+  const uint32_t resid_bar = bar_base + 8u * (2 * kMaxStages + 5);  // TMA-fetched residual tile landed
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_seg; ++s) tma_prefetch_desc(&p.a_map[p.seg_a[s]]);
@@ -199,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), CG * (kEpiThreads / 32));  // one arrival per epilogue warp of every CTA
     }
+    mbar_init(resid_bar, 1);
     fence_mbar_init();
   }
   if (CG == 2) cluster_sync_all();  // peer barriers initialised before anyone signals them; both CTAs alive
@@ -291,8 +299,13 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-          if (CG == 2) umma_bf16_2sm(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          else umma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+#ifdef EVC_GEMM_PROF
+          const uint32_t td = tmem_d ^ ((p.exp_alt && (k & 1)) ? static_cast<uint32_t>(kAccStride) : 0u);
+#else
+          const uint32_t td = tmem_d;
+#endif
+          if (CG == 2) umma_bf16_2sm(td, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          else umma_bf16(td, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         if (CG == 2) {
           umma_commit_2sm(empty_bar(stage), 3);  // frees this stage in both CTAs
@@ -327,18 +340,17 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     const int dy = (row / p.TW) % p.TH;
     const int db = row / (p.TW * p.TH);
     uint8_t* gsm = smem_raw + (base - smem_u32(smem_raw));
-    float* sbias = reinterpret_cast<float*>(gsm + (bar_base - base) + 256);
+    uint8_t* tail = gsm + (bar_base - base);
+    float* sbias = reinterpret_cast<float*>(tail + 256);
     const uint32_t res_pitch = static_cast<uint32_t>(p.BN) * 2u + 16u;
-    uint8_t* sres = gsm + (bar_base - base) + 256 + 1024 + static_cast<size_t>(row) * res_pitch;
-    const uint32_t sres_u32 = bar_base + 256u + 1024u + static_cast<uint32_t>(row) * res_pitch;
-    // [4 warps][BN][2] floats, after the residual rows
-    float* sstat = reinterpret_cast<float*>(gsm + (bar_base - base) + 256 + 1024 + (p.resid_smem ? 128u * res_pitch : 0u));
-    // TMA-store staging: [8 warps][tma_out buffers][32 rows x 64 B], 64 B swizzle, after the statistics scratch
-    const uint32_t stg_off = (bar_base - base) + 256u + 1024u + (p.resid_smem ? 128u * res_pitch : 0u) +
-                             (p.stats != nullptr ? 32u * static_cast<uint32_t>(p.BN) : 0u);
-    const uint32_t stg_al = (stg_off + 1023u) & ~1023u;
-    uint8_t* stg_base = gsm + stg_al + static_cast<uint32_t>(warp - 4) * static_cast<uint32_t>(p.tma_out) * 2048u;
-    const uint32_t stg_base_u32 = base + stg_al + static_cast<uint32_t>(warp - 4) * static_cast<uint32_t>(p.tma_out) * 2048u;
+    uint8_t* sres = tail + p.off_resid + static_cast<size_t>(row) * res_pitch;
+    const uint32_t sres_u32 = bar_base + p.off_resid + static_cast<uint32_t>(row) * res_pitch;
+    // TMA-fetched residual: [BN/64 panels][128 rows][128 B], 128 B swizzle
+    const uint8_t* sres_t = tail + p.off_resid + row * 128;
+    float* sstat = reinterpret_cast<float*>(tail + p.off_stat);  // [4 warps][BN][2] floats
+    // TMA-store staging: [8 warps][tma_out buffers][32 rows x 64 B], 64 B swizzle
+    uint8_t* stg_base = tail + p.off_stage + static_cast<uint32_t>(warp - 4) * static_cast<uint32_t>(p.tma_out) * 2048u;
+    const uint32_t stg_base_u32 = bar_base + p.off_stage + static_cast<uint32_t>(warp - 4) * static_cast<uint32_t>(p.tma_out) * 2048u;
     int stg_i = 0;
     int it = 0;
     PROF_DECL(long long w_tfull = 0; long long w_pre = 0; long long w_ld = 0; long long w_rest = 0;)
@@ -360,7 +372,16 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       if (p.bias != nullptr) {
         for (int j = e; j < p.BN; j += kEpiThreads) sbias[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
       }
-      if (resid_fast && valid) {
+      if (p.resid_tma) {
+        if (e == 0) {
+          const int panels = (p.BN + 63) >> 6;
+          const long long tile_pix = ((long long)b0 * p.H + y0) * p.W + x0;
+          mbar_expect_tx(resid_bar, static_cast<uint32_t>(panels) * 16384u);
+          for (int pn = 0; pn < panels; ++pn)
+            tma_load_2d(&p.resid_map, bar_base + p.off_resid + pn * 16384, resid_bar, n0 + 64 * pn,
+                        static_cast<int>(tile_pix));
+        }
+      } else if (resid_fast && valid) {
         const __nv_bfloat16* r = p.resid + pix * p.resid_ld + n0;
         for (int c0 = grp * 32; c0 < p.BN; c0 += 64)  // only the chunks this thread will consume
 #pragma unroll
@@ -377,6 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       PROF_ADD(w_tfull, t_tf);
       tc_fence_after();
       asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (p.resid_tma) mbar_wait(resid_bar, static_cast<uint32_t>(it) & 1u);
       const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
       bool released = false;
       for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
@@ -417,7 +439,22 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
               f[j + 3] += bv.w;
             }
           }
-          if (resid_fast) {
+          if (p.resid_tma) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const int col = c0 + j;
+              const uint4 u = *reinterpret_cast<const uint4*>(sres_t + (col >> 6) * 16384 +
+                                                              ((((col & 63) >> 3) ^ (row & 7)) << 4));
+              f[j + 0] += bf16_lo(u.x);
+              f[j + 1] += bf16_hi(u.x);
+              f[j + 2] += bf16_lo(u.y);
+              f[j + 3] += bf16_hi(u.y);
+              f[j + 4] += bf16_lo(u.z);
+              f[j + 5] += bf16_hi(u.z);
+              f[j + 6] += bf16_lo(u.w);
+              f[j + 7] += bf16_hi(u.w);
+            }
+          } else if (resid_fast) {
             if (valid) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
@@ -834,30 +871,63 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     delete pl;
     return evc_set_error(EVC_ERR_INVALID, "fused GroupNorm statistics need bf16 row output and H*W % 32 == 0");
   }
-  int tail_bytes = 256 + 1024 + (p.resid_smem ? 128 * (d->bn * 2 + 16) : 0) + (d->stats ? 32 * d->bn : 0);
   // TMA-store epilogue (see the kernel): bf16 rows, whole 128-row tiles, 32-column chunks
-  static int tma_env = -1;
+  static int tma_env = -1, rtma_env = -1;
   if (tma_env < 0) {
     const char* e = getenv("EVC_GEMM_TMA_STORE");
     tma_env = e ? atoi(e) : 2;
+    e = getenv("EVC_GEMM_TMA_RESID");
+    rtma_env = e ? atoi(e) : 1;
   }
-  p.tma_out = 0;
   const long long m_total = (long long)d->B * d->H * d->W;
-  if (tma_env > 0 && !split && d->out_mode == EVC_OUT_BF16_ROWS && p.rows_valid == 128 && (d->bn % 32) == 0 &&
-      (d->out_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 && m_total < (1ll << 31)) {
+  const bool can_tma_out = tma_env > 0 && !split && d->out_mode == EVC_OUT_BF16_ROWS && p.rows_valid == 128 &&
+                           (d->bn % 32) == 0 && (d->out_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 &&
+                           m_total < (1ll << 31);
+  p.resid_tma = (can_tma_out && rtma_env > 0 && d->resid != nullptr && (d->resid_ld % 8) == 0 &&
+                 (reinterpret_cast<uintptr_t>(d->resid) & 15) == 0) ? 1 : 0;
+  if (p.resid_tma) p.resid_smem = 0;
+  // scratch behind the barrier block: [barriers 256 B][bias 1 KB][residual][statistics][store staging]
+  auto layout = [&](int nbuf) {
+    int off = 256 + 1024;
+    if (p.resid_tma) {
+      off = (off + 1023) & ~1023;
+      p.off_resid = off;
+      off += ((d->bn + 63) / 64) * 16384;
+    } else {
+      p.off_resid = off;
+      if (p.resid_smem) off += 128 * (d->bn * 2 + 16);
+    }
+    p.off_stat = off;
+    if (d->stats) off += 32 * d->bn;
+    if (nbuf > 0) {
+      off = (off + 1023) & ~1023;
+      p.off_stage = off;
+      off += 8 * nbuf * 2048;
+    }
+    return off;
+  };
+  p.tma_out = 0;
+#ifdef EVC_GEMM_PROF
+  p.exp_alt = getenv("EVC_EXP_ALT") ? atoi(getenv("EVC_EXP_ALT")) : 0;
+#endif
+  if (can_tma_out) {
     uint64_t dims[2] = {(uint64_t)d->w_rows, (uint64_t)m_total};
     uint64_t strides[1] = {(uint64_t)d->out_ld * 2};
     uint32_t box[2] = {32, 32};
     int rc = encode_map(&p.out_map, d->out, 2, dims, strides, box, 1, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc == EVC_OK && p.resid_tma) {
+      uint64_t rstrides[1] = {(uint64_t)d->resid_ld * 2};
+      uint32_t rbox[2] = {64, 128};
+      rc = encode_map(&p.resid_map, d->resid, 2, dims, rstrides, rbox);
+    }
     if (rc != EVC_OK) {
       delete pl;
       return rc;
     }
     // two staging buffers per epilogue warp unless that would leave fewer than four pipeline stages
-    const int tail2 = tail_bytes + 1024 + 8 * 2 * 2048;
-    p.tma_out = (tma_env >= 2 && (227 * 1024 - 1024 - tail2) / stage_bytes >= 4) ? 2 : 1;
-    tail_bytes += 1024 + 8 * p.tma_out * 2048;
+    p.tma_out = (tma_env >= 2 && (227 * 1024 - 1024 - layout(2)) / stage_bytes >= 4) ? 2 : 1;
   }
+  const int tail_bytes = layout(p.tma_out);
   const int budget = 227 * 1024 - 1024 /*align slack*/ - tail_bytes;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;

@@ -9,7 +9,9 @@ import torch
 from evcdiff import ops, _lib
 
 lib = _lib.load()
-lib.evc_gemm_prof_read.argtypes = [C.POINTER(C.c_uint64)]
+HAVE_PROF = hasattr(lib, "evc_gemm_prof_read")
+if HAVE_PROF:
+    lib.evc_gemm_prof_read.argtypes = [C.POINTER(C.c_uint64)]
 DEV = "cuda"
 B = int(os.environ.get("B", "46"))
 
@@ -27,23 +29,35 @@ def run(name, H, Cins, N, taps=9, resid=False, stats=False, cg=None, reps=5):
         plan.launch()
     torch.cuda.synchronize()
     buf = (C.c_uint64 * 16)()
-    lib.evc_gemm_prof_read(buf)
+    if HAVE_PROF:
+        lib.evc_gemm_prof_read(buf)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
         plan.launch()
     e1.record()
     torch.cuda.synchronize()
-    lib.evc_gemm_prof_read(buf)
-    v = [float(x) for x in buf]
     ms = e0.elapsed_time(e1) / reps
     tf = plan.flops / ms / 1e9
+    if not HAVE_PROF:
+        print(f"{name:34s} cg={plan.cta_group} {ms:7.3f} ms {tf:7.1f} TF", flush=True)
+        return
+    lib.evc_gemm_prof_read(buf)
+    v = [float(x) for x in buf]
     print(f"{name:34s} cg={plan.cta_group} {ms:7.3f} ms {tf:7.1f} TF | MMA thread: operands-wait {100 * v[1] / v[0]:5.1f}% "
           f"accumulator-wait {100 * v[2] / v[0]:5.1f}% issue {100 * (v[0] - v[1] - v[2]) / v[0]:5.1f}% | producer waits for a free "
           f"stage {100 * v[4] / v[3]:5.1f}% | epilogue: waits for the accumulator {100 * v[6] / v[5]:5.1f}%, prefetch+bar.sync "
           f"{100 * v[8] / v[5]:5.1f}%, tcgen05.ld {100 * v[9] / v[5]:5.1f}%, math+stores+stats {100 * v[10] / v[5]:5.1f}%", flush=True)
 
 
+if os.environ.get("NSWEEP"):
+    # does the tensor pipe run faster with a wider N tile?  (shared-memory bandwidth model, profiles/r01_notes.md)
+    for n in (64, 96, 128, 192, 256):
+        run(f"128^2 192->{n} 3x3", 128, [192], n)
+        run(f"128^2 192->{n} 3x3 cg1", 128, [192], n, cg=1)
+    for n in (192, 256):
+        run(f"128^2 1x1 K=1728 ->{n}", 128, [1728], n, taps=1)
+    sys.exit(0)
 run("128^2 192->192", 128, [192], 192)
 run("128^2 192->192 +stats", 128, [192], 192, stats=True)
 run("128^2 192->192 +resid", 128, [192], 192, resid=True)
