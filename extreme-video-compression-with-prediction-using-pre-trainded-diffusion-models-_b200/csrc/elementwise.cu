@@ -240,18 +240,18 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
   }
   __syncthreads();
   // group statistics: one thread per group, channels summed in index order (deterministic)
-  if (tid < groups) {
+  for (int gi = tid; gi < groups; gi += nthr) {
     float s = 0.f, q = 0.f;
     for (int j = 0; j < cpg; ++j) {
-      const float2 t = s_ch[tid * cpg + j];
+      const float2 t = s_ch[gi * cpg + j];
       s += t.x;
       q += t.y;
     }
     const float inv_n = 1.f / ((float)cpg * (float)HW);
     const float mean = s * inv_n;
     const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-    s_mean[tid] = mean;
-    s_rstd[tid] = rsqrtf(var + eps);
+    s_mean[gi] = mean;
+    s_rstd[gi] = rsqrtf(var + eps);
   }
   __syncthreads();
   float a[8], bb[8];
@@ -431,6 +431,215 @@ __global__ void fir_down_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
     }
     fir_store<SPLIT>(y + (((long long)b * OH + oy) * OW + ox) * C + v * 8, y_lo_off, acc);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused res-block prologue of the up / down blocks (layerspp.py:598-611): from ONE read of the block input
+// x = [x0 | x1] produce  y_act = FIR(SiLU(AdaGN(x)))  and  y_raw = FIR(x)  (the skip path), instead of
+// gn_apply -> fir(h) + fir(x) (three reads, one full-size intermediate).  A thread owns 8 channels of one pixel
+// column and walks down a strip of rows with a two-row rolling window of horizontally filtered values, so every
+// input vector is loaded once per column neighbourhood (3 loads per input row when up-sampling, 8 per output row
+// when down-sampling).  Zero padding applies after the activation, exactly like upfirdn2d on h.
+// grid = (column blocks, row strips, B), block = (nvec, PX).
+// ---------------------------------------------------------------------------------------------
+struct GnFirArgs {
+  const __nv_bfloat16 *x0, *x1;
+  int C0, C1, H, W;
+  const long long *stats0, *stats1;
+  int groups;
+  float eps;
+  const float* ss;
+  int adagn;
+  __nv_bfloat16 *y_act, *y_raw0, *y_raw1;
+  int strip;  // rows per block: input rows (up) / output rows (down)
+};
+
+__device__ __forceinline__ void act8(const float (&x)[8], const float (&a)[8], const float (&bb)[8], float (&y)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) y[j] = fmaf(x[j], a[j], bb[j]);
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) silu_pair(y[j], y[j + 1]);
+}
+
+template <bool UP>
+__global__ void __launch_bounds__(256, 2) gn_fir_kernel(const GnFirArgs g) {
+  __shared__ float s_mean[64], s_rstd[64];
+  __shared__ float2 s_ch[2048];
+  pdl_wait();
+  pdl_trigger();
+  const int C = g.C0 + g.C1, H = g.H, W = g.W;
+  const int b = blockIdx.z;
+  const int cpg = C / g.groups;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  const int c = threadIdx.x * 8;
+  // ---- GroupNorm coefficients of this thread's 8 channels (same arithmetic as gn_apply_kernel)
+  for (int cc = tid; cc < C; cc += nthr) {
+    const longlong2 st = *reinterpret_cast<const longlong2*>(
+        (cc < g.C0) ? g.stats0 + ((long long)b * g.C0 + cc) * 2 : g.stats1 + ((long long)b * g.C1 + (cc - g.C0)) * 2);
+    s_ch[cc] = make_float2((float)((double)st.x * (1.0 / 1048576.0)), (float)((double)st.y * (1.0 / 1048576.0)));
+  }
+  float gam[8], bet[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(g.ss + c), g1 = *reinterpret_cast<const float4*>(g.ss + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(g.ss + C + c), b1 = *reinterpret_cast<const float4*>(g.ss + C + c + 4);
+    gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
+    bet[0] = b0.x; bet[1] = b0.y; bet[2] = b0.z; bet[3] = b0.w; bet[4] = b1.x; bet[5] = b1.y; bet[6] = b1.z; bet[7] = b1.w;
+  }
+  __syncthreads();
+  for (int gi = tid; gi < g.groups; gi += nthr) {  // blocks can be narrower than the group count
+    float s = 0.f, q = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      const float2 t = s_ch[gi * cpg + j];
+      s += t.x;
+      q += t.y;
+    }
+    const float inv_n = 1.f / ((float)cpg * (float)(H * W));
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    s_mean[gi] = mean;
+    s_rstd[gi] = rsqrtf(var + g.eps);
+  }
+  __syncthreads();
+  float a[8], bb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int gi = (c + j) / cpg;
+    a[j] = s_rstd[gi] * (g.adagn ? (1.f + gam[j]) : gam[j]);
+    bb[j] = bet[j] - s_mean[gi] * a[j];
+  }
+  const bool first = (c < g.C0);
+  const int Cs = first ? g.C0 : g.C1;      // channels of the source / raw destination tensor of this thread
+  const int cs = first ? c : c - g.C0;     // channel offset inside it
+  const __nv_bfloat16* xs = (first ? g.x0 : g.x1) + (long long)b * H * W * Cs + cs;
+  __nv_bfloat16* yr = first ? g.y_raw0 : g.y_raw1;
+  const int px = blockIdx.x * blockDim.y + threadIdx.y;  // input column (up) / output column (down)
+  const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+  if (UP) {
+    if (px >= W) return;
+    const int OW = 2 * W;
+    const int r0 = blockIdx.y * g.strip, r1 = min(H, r0 + g.strip);
+    __nv_bfloat16* ya = g.y_act + (long long)b * 4 * H * W * C + c;
+    yr += (long long)b * 4 * H * W * Cs + cs;
+    // horizontally filtered row r: L = (x[px-1] + 3 x[px]) / 4, R = (3 x[px] + x[px+1]) / 4, raw and activated
+    float pl[8], pr[8], pal[8], par[8];  // previous row
+    auto hrow = [&](int r, float (&l)[8], float (&rr)[8], float (&al)[8], float (&ar)[8]) {
+      if (r < 0 || r >= H) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) l[j] = rr[j] = al[j] = ar[j] = 0.f;
+        return;
+      }
+      const __nv_bfloat16* row = xs + ((long long)r * W + px) * Cs;
+      float m[8], c0[8], p[8], am[8], ac[8], ap[8];
+      unpack8(ld_ro16(row), c0);
+      act8(c0, a, bb, ac);
+      if (px > 0) {
+        unpack8(ld_ro16(row - Cs), m);
+        act8(m, a, bb, am);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = am[j] = 0.f;
+      }
+      if (px + 1 < W) {
+        unpack8(ld_ro16(row + Cs), p);
+        act8(p, a, bb, ap);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[j] = ap[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        l[j] = 0.25f * m[j] + 0.75f * c0[j];
+        rr[j] = 0.75f * c0[j] + 0.25f * p[j];
+        al[j] = 0.25f * am[j] + 0.75f * ac[j];
+        ar[j] = 0.75f * ac[j] + 0.25f * ap[j];
+      }
+    };
+    auto emit = [&](int oy, float wp, float wc, const float (&cl)[8], const float (&cr)[8], const float (&cal)[8],
+                    const float (&car)[8]) {
+      float o[8];
+      const long long pix = ((long long)oy * OW + 2 * px);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = wp * pl[j] + wc * cl[j];
+      *reinterpret_cast<uint4*>(yr + pix * Cs) = pack8(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = wp * pr[j] + wc * cr[j];
+      *reinterpret_cast<uint4*>(yr + (pix + 1) * Cs) = pack8(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = wp * pal[j] + wc * cal[j];
+      *reinterpret_cast<uint4*>(ya + pix * C) = pack8(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = wp * par[j] + wc * car[j];
+      *reinterpret_cast<uint4*>(ya + (pix + 1) * C) = pack8(o);
+    };
+    hrow(r0 - 1, pl, pr, pal, par);
+    // step r (r0 .. r1): rows r-1 and r are known -> output rows 2r-1 (if r > r0) and 2r (if r < r1)
+    for (int r = r0; r <= r1; ++r) {
+      float cl[8], cr[8], cal[8], car[8];
+      hrow(r, cl, cr, cal, car);
+      if (r > r0) emit(2 * r - 1, 0.75f, 0.25f, cl, cr, cal, car);
+      if (r < r1) emit(2 * r, 0.25f, 0.75f, cl, cr, cal, car);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        pl[j] = cl[j];
+        pr[j] = cr[j];
+        pal[j] = cal[j];
+        par[j] = car[j];
+      }
+    }
+  } else {
+    const int OH = H / 2, OW = W / 2;
+    if (px >= OW) return;
+    const int o0 = blockIdx.y * g.strip, o1 = min(OH, o0 + g.strip);
+    __nv_bfloat16* ya = g.y_act + (long long)b * OH * OW * C + c;
+    yr += (long long)b * OH * OW * Cs + cs;
+    // horizontally filtered row r at output column px: (x[2px-1] + 3 x[2px] + 3 x[2px+1] + x[2px+2]) / 8
+    auto hrow = [&](int r, float (&h)[8], float (&ah)[8]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = ah[j] = 0.f;
+      if (r < 0 || r >= H) return;
+      const __nv_bfloat16* row = xs + (long long)r * W * Cs;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int xx = 2 * px - 1 + t;
+        if (xx < 0 || xx >= W) continue;
+        const float w = (t == 0 || t == 3) ? 0.125f : 0.375f;
+        float v[8], av[8];
+        unpack8(ld_ro16(row + (long long)xx * Cs), v);
+        act8(v, a, bb, av);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          h[j] = fmaf(w, v[j], h[j]);
+          ah[j] = fmaf(w, av[j], ah[j]);
+        }
+      }
+    };
+    float h0[8], ah0[8], h1[8], ah1[8];  // rows 2oy-1 and 2oy
+    hrow(2 * o0 - 1, h0, ah0);
+    hrow(2 * o0, h1, ah1);
+    for (int oy = o0; oy < o1; ++oy) {
+      float h2[8], ah2[8], h3[8], ah3[8];
+      hrow(2 * oy + 1, h2, ah2);
+      hrow(2 * oy + 2, h3, ah3);
+      float o[8];
+      const long long pix = (long long)oy * OW + px;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.125f * h0[j] + 0.375f * h1[j] + 0.375f * h2[j] + 0.125f * h3[j];
+      *reinterpret_cast<uint4*>(yr + pix * Cs) = pack8(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.125f * ah0[j] + 0.375f * ah1[j] + 0.375f * ah2[j] + 0.125f * ah3[j];
+      *reinterpret_cast<uint4*>(ya + pix * C) = pack8(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        h0[j] = h2[j];
+        ah0[j] = ah2[j];
+        h1[j] = h3[j];
+        ah1[j] = ah3[j];
+      }
+    }
+  }
+  (void)z8;
 }
 
 __global__ void nearest_up2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
@@ -654,6 +863,46 @@ static int gn_apply_impl(const void* x0, const void* x0_lo, int32_t C0, const vo
                               reinterpret_cast<const __nv_bfloat16*>(x1_lo), reinterpret_cast<__nv_bfloat16*>(y_lo));
   if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
   return evc_check_launch("gn_apply_kernel");
+}
+
+extern "C" int evc_gn_fir(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int32_t H, int32_t W,
+                          const int64_t* stats0, const int64_t* stats1, int32_t groups, float eps, const float* ss,
+                          int32_t adagn, int32_t up, void* y_act, void* y_raw0, void* y_raw1, evc_stream_t stream) {
+  if (!x0 || !stats0 || !ss || !y_act || !y_raw0 || B < 1 || H < 1 || W < 1 || C0 < 8 || (C0 % 8) || (C1 % 8) ||
+      (x1 == nullptr) != (C1 == 0) || (x1 != nullptr && (!stats1 || !y_raw1)) || groups < 1 || groups > 64 ||
+      ((C0 + C1) % groups) || (!up && ((H | W) & 1)))
+    return evc_set_error(EVC_ERR_INVALID, "evc_gn_fir: bad arguments");
+  const int C = C0 + C1, nvec = C / 8;
+  if (nvec > 256) return evc_set_error(EVC_ERR_INVALID, "evc_gn_fir: C > 2048");
+  const void* ptrs[7] = {x0, x1, stats0, stats1, ss, y_act, y_raw0};
+  for (int i = 0; i < 7; ++i)
+    if (reinterpret_cast<uintptr_t>(ptrs[i]) & 15) return evc_set_error(EVC_ERR_INVALID, "evc_gn_fir: pointers must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(y_raw1) & 15) return evc_set_error(EVC_ERR_INVALID, "evc_gn_fir: pointers must be 16-byte aligned");
+  GnFirArgs g;
+  g.x0 = reinterpret_cast<const __nv_bfloat16*>(x0);
+  g.x1 = reinterpret_cast<const __nv_bfloat16*>(x1);
+  g.C0 = C0; g.C1 = C1; g.H = H; g.W = W;
+  g.stats0 = reinterpret_cast<const long long*>(stats0);
+  g.stats1 = reinterpret_cast<const long long*>(stats1);
+  g.groups = groups; g.eps = eps; g.ss = ss; g.adagn = adagn;
+  g.y_act = reinterpret_cast<__nv_bfloat16*>(y_act);
+  g.y_raw0 = reinterpret_cast<__nv_bfloat16*>(y_raw0);
+  g.y_raw1 = reinterpret_cast<__nv_bfloat16*>(y_raw1);
+  int pxb = 256 / nvec;
+  if (pxb < 1) pxb = 1;
+  const int cols = up ? W : W / 2, rows = up ? H : H / 2;
+  if (pxb > cols) pxb = cols;
+  // strips: enough blocks for ~4 per SM, at least 4 rows each (the window warm-up costs 1 (up) / 2 (down) rows)
+  const int xb = (cols + pxb - 1) / pxb;
+  int strip = 16;
+  while (strip > 4 && (long long)xb * ((rows + strip - 1) / strip) * B < 4ll * evc_num_sms()) strip >>= 1;
+  if (strip > rows) strip = rows;
+  g.strip = strip;
+  dim3 grid(xb, (rows + strip - 1) / strip, B), block(nvec, pxb);
+  cudaError_t le = up ? evc_launch(gn_fir_kernel<true>, grid, block, 0, (cudaStream_t)stream, 1, g)
+                      : evc_launch(gn_fir_kernel<false>, grid, block, 0, (cudaStream_t)stream, 1, g);
+  if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
+  return evc_check_launch("gn_fir_kernel");
 }
 
 static int fir_impl(const void* x, const void* x_lo, void* y, void* y_lo, int32_t B, int32_t H, int32_t W, int32_t C,

@@ -77,6 +77,7 @@ SIGNATURES = {
     "evc_softmax_rows_split": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "evc_pack_nchw_split": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _i32, _i32, _vp]),
     "evc_fir_resample": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "evc_gn_fir": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "evc_nearest_up2": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "evc_softmax_rows": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "evc_timestep_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),

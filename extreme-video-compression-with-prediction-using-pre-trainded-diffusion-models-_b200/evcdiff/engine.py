@@ -215,6 +215,26 @@ class EngineBase:
             self._op(lambda li: plan.launch(bias_fn(li)), "gemm", meta)
         return plan
 
+    def gn_fir(self, xa, xb, ss_fn, eps, adagn, up):
+        """Fused prologue of an up / down res block: returns (FIR(SiLU(GN([xa|xb]))), [FIR(xa), FIR(xb)])."""
+        self.ensure_stats(xa)
+        if xb is not None:
+            self.ensure_stats(xb)
+        C = xa.C + (xb.C if xb is not None else 0)
+        groups = self.fixed_groups or gn_groups(C)
+        H2, W2 = (xa.H * 2, xa.W * 2) if up else (xa.H // 2, xa.W // 2)
+        h = self.new_act(H2, W2, C)
+        ra = self.new_act(H2, W2, xa.C)
+        rb = self.new_act(H2, W2, xb.C) if xb is not None else None
+
+        def run(li):
+            ops.gn_fir(xa.t, xa.C, xb.t if xb is not None else None, xb.C if xb is not None else 0, xa.B, xa.H, xa.W,
+                       self._stats_view(xa), self._stats_view(xb) if xb is not None else None, groups, eps, ss_fn(li),
+                       adagn, up, h.t, ra.t, rb.t if rb is not None else None)
+        nin = xa.t.numel() + (xb.t.numel() if xb is not None else 0)
+        self._op(run, "gn_fir", dict(bytes=(nin + 2 * h.t.numel()) * 2))
+        return h, [ra] + ([rb] if rb is not None else [])
+
     def fir(self, a, up):
         H2, W2 = (a.H * 2, a.W * 2) if up else (a.H // 2, a.W // 2)
         out = self.new_act(H2, W2, a.C)
@@ -461,11 +481,16 @@ class NCSNppEngine(EngineBase):
         sd, P, dev = self.sd, self.P, self.device
         cin, cout = s["cin"], s["cout"]
         assert cin == xa.C + (xb.C if xb is not None else 0)
-        h = self.new_act(xa.H, xa.W, cin)
-        self.gn_apply(xa, xb, self._ss(i, 0), 1e-5, True, True, h)
         xs = [xa] + ([xb] if xb is not None else [])
         tmp = []
-        if s["up"] or s["down"]:
+        fused = (s["up"] or s["down"]) and not self.split and os.environ.get("EVC_GN_FIR", "1") != "0"
+        if fused:
+            h, xs = self.gn_fir(xa, xb, self._ss(i, 0), 1e-5, True, s["up"])
+            tmp += xs
+        else:
+            h = self.new_act(xa.H, xa.W, cin)
+            self.gn_apply(xa, xb, self._ss(i, 0), 1e-5, True, True, h)
+        if (s["up"] or s["down"]) and not fused:
             h2 = self.fir(h, s["up"])
             self.release(h)
             h = h2

@@ -229,6 +229,13 @@ def fir_resample(x, y, B, H, W, C, up, x_lo=None, y_lo=None):
               "evc_fir_resample_split")
 
 
+def gn_fir(x0, C0, x1, C1, B, H, W, stats0, stats1, groups, eps, ss, adagn, up, y_act, y_raw0, y_raw1):
+    """y_act = FIR(SiLU(GN([x0|x1]))), y_raw{0,1} = FIR(x{0,1}) from one read of the inputs (up / down res blocks)."""
+    _require_cuda(x0, x1, stats0, stats1, ss, y_act, y_raw0, y_raw1)
+    check(load().evc_gn_fir(_ptr(x0), C0, _ptr(x1), C1, B, H, W, _ptr(stats0), _ptr(stats1), groups, eps, _ptr(ss),
+                            int(adagn), int(up), _ptr(y_act), _ptr(y_raw0), _ptr(y_raw1), stream_ptr()), "evc_gn_fir")
+
+
 def nearest_up2(x, y, B, H, W, C):
     _require_cuda(x, y)
     check(load().evc_nearest_up2(_ptr(x), _ptr(y), B, H, W, C, stream_ptr()), "evc_nearest_up2")

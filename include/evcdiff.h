@@ -195,6 +195,14 @@ int evc_pack_nchw_split(const void* src, int32_t src_is_f64, int32_t B, int32_t 
 int evc_fir_resample(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, int32_t up,
                      evc_stream_t stream);
 
+/* Fused prologue of the up / down res blocks (layerspp.py:598-611: h = act(GN(x)); h = resample(h); x = resample(x)):
+ * one read of x = [x0 | x1] produces y_act = FIR(SiLU(GN(x) * gamma' + beta')) (B,H',W',C0+C1) and the resampled skip
+ * inputs y_raw0 (B,H',W',C0), y_raw1 (B,H',W',C1).  Arguments as evc_gn_apply / evc_fir_resample; the activation is
+ * not rounded to bf16 before the filter.  Zero padding applies after the activation, as in upfirdn2d(h). */
+int evc_gn_fir(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int32_t H, int32_t W,
+               const int64_t* stats0, const int64_t* stats1, int32_t groups, float eps, const float* ss, int32_t adagn,
+               int32_t up, void* y_act, void* y_raw0, void* y_raw1, evc_stream_t stream);
+
 /* nearest-neighbour x2 upsample, NHWC bf16 (models/unet.py:123-131) */
 int evc_nearest_up2(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, evc_stream_t stream);
 

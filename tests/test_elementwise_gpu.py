@@ -76,6 +76,42 @@ def test_fir(B, H, C):
     assert common.rel_l2(nchw(dn), O.fir_down2(nchw(x))) < 4e-3
 
 
+@pytest.mark.parametrize("B,H,C0,C1,up", [
+    (2, 16, 192, 0, True), (2, 16, 192, 0, False), (3, 8, 768, 576, True), (2, 32, 384, 192, True),
+    (2, 32, 384, 192, False), (1, 64, 192, 0, False), (1, 64, 192, 192, True), (2, 4, 64, 32, True), (2, 4, 64, 32, False),
+    (1, 34, 192, 0, False), (1, 20, 64, 0, True), (2, 2, 96, 0, False), (2, 1, 128, 96, True), (2, 2, 96, 64, True),
+])
+def test_gn_fir_fused(B, H, C0, C1, up):
+    """FIR(SiLU(AdaGN([x0|x1]))) and FIR(x) from one kernel (up / down res-block prologue, layerspp.py:598-611)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(4)
+    C = C0 + C1
+    x0 = nhwc(torch.randn(B, C0, H, H, device=DEV, generator=g) * 1.7 + 0.3)
+    x1 = nhwc(torch.randn(B, C1, H, H, device=DEV, generator=g) * 0.6 - 0.2) if C1 else None
+    ss = torch.randn(2 * C, device=DEV, generator=g) * 0.3
+    st0 = torch.zeros(B, C0, 2, device=DEV, dtype=torch.int64)
+    ops.gn_stats(x0, B, H * H, C0, st0)
+    st1 = None
+    if C1:
+        st1 = torch.zeros(B, C1, 2, device=DEV, dtype=torch.int64)
+        ops.gn_stats(x1, B, H * H, C1, st1)
+    H2 = 2 * H if up else H // 2
+    ya = torch.full((B, H2, H2, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    r0 = torch.full((B, H2, H2, C0), float("nan"), device=DEV, dtype=torch.bfloat16)
+    r1 = torch.full((B, H2, H2, C1), float("nan"), device=DEV, dtype=torch.bfloat16) if C1 else None
+    groups = O.gn_groups(C)
+    ops.gn_fir(x0, C0, x1, C1, B, H, H, st0, st1, groups, 1e-5, ss, True, up, ya, r0, r1)
+    torch.cuda.synchronize()
+    xc = torch.cat([nchw(x0)] + ([nchw(x1)] if C1 else []), 1)
+    h = F.group_norm(xc, groups, None, None, eps=1e-5)
+    h = F.silu(h * (1 + ss[:C]).view(1, C, 1, 1) + ss[C:].view(1, C, 1, 1))
+    fir = O.fir_up2 if up else O.fir_down2
+    assert common.rel_l2(nchw(ya), fir(h)) < 4e-3
+    assert common.rel_l2(nchw(r0), fir(nchw(x0))) < 4e-3
+    if C1:
+        assert common.rel_l2(nchw(r1), fir(nchw(x1))) < 4e-3
+
+
 def test_nearest_up():
     ops = _ops()
     x = nhwc(torch.randn(2, 64, 8, 8, device=DEV))
