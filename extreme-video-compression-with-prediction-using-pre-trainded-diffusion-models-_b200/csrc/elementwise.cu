@@ -454,15 +454,42 @@ struct GnFirArgs {
   int strip;  // rows per block: input rows (up) / output rows (down)
 };
 
-__device__ __forceinline__ void act8(const float (&x)[8], const float (&a)[8], const float (&bb)[8], float (&y)[8]) {
+// V channels (8 or 4) per thread: 16- / 8-byte vectors.  V = 4 halves the register footprint (twice the resident warps),
+// which is what the load-latency-bound walk needs at the high-resolution levels.
+template <int V>
+__device__ __forceinline__ void ldv(const __nv_bfloat16* p, float (&f)[V]) {
+  if (V == 8) {
+    const uint4 u = ld_ro16(p);
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4 % V] = bf16_lo(u.z); f[5 % V] = bf16_hi(u.z); f[6 % V] = bf16_lo(u.w); f[7 % V] = bf16_hi(u.w);
+  } else {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  }
+}
+template <int V>
+__device__ __forceinline__ void stv(__nv_bfloat16* p, const float (&f)[V]) {
+  if (V == 8) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4 % V], f[5 % V]); u.w = pack_bf16x2(f[6 % V], f[7 % V]);
+    *reinterpret_cast<uint4*>(p) = u;
+  } else {
+    uint2 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+}
+template <int V>
+__device__ __forceinline__ void actv(const float (&x)[V], const float (&a)[V], const float (&bb)[V], float (&y)[V]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) y[j] = fmaf(x[j], a[j], bb[j]);
+  for (int j = 0; j < V; ++j) y[j] = fmaf(x[j], a[j], bb[j]);
 #pragma unroll
-  for (int j = 0; j < 8; j += 2) silu_pair(y[j], y[j + 1]);
+  for (int j = 0; j < V; j += 2) silu_pair(y[j], y[j + 1]);
 }
 
-template <bool UP>
-__global__ void __launch_bounds__(256, 2) gn_fir_kernel(const GnFirArgs g) {
+template <bool UP, int V>
+__global__ void __launch_bounds__(256, (V == 8) ? 2 : 3) gn_fir_kernel(const GnFirArgs g) {
   __shared__ float s_mean[64], s_rstd[64];
   __shared__ float2 s_ch[2048];
   pdl_wait();
@@ -472,19 +499,20 @@ __global__ void __launch_bounds__(256, 2) gn_fir_kernel(const GnFirArgs g) {
   const int cpg = C / g.groups;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int nthr = blockDim.x * blockDim.y;
-  const int c = threadIdx.x * 8;
-  // ---- GroupNorm coefficients of this thread's 8 channels (same arithmetic as gn_apply_kernel)
+  const int c = threadIdx.x * V;
+  // ---- GroupNorm coefficients of this thread's channels (same arithmetic as gn_apply_kernel)
   for (int cc = tid; cc < C; cc += nthr) {
     const longlong2 st = *reinterpret_cast<const longlong2*>(
         (cc < g.C0) ? g.stats0 + ((long long)b * g.C0 + cc) * 2 : g.stats1 + ((long long)b * g.C1 + (cc - g.C0)) * 2);
     s_ch[cc] = make_float2((float)((double)st.x * (1.0 / 1048576.0)), (float)((double)st.y * (1.0 / 1048576.0)));
   }
-  float gam[8], bet[8];
-  {
-    const float4 g0 = *reinterpret_cast<const float4*>(g.ss + c), g1 = *reinterpret_cast<const float4*>(g.ss + c + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(g.ss + C + c), b1 = *reinterpret_cast<const float4*>(g.ss + C + c + 4);
-    gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
-    bet[0] = b0.x; bet[1] = b0.y; bet[2] = b0.z; bet[3] = b0.w; bet[4] = b1.x; bet[5] = b1.y; bet[6] = b1.z; bet[7] = b1.w;
+  float gam[V], bet[V];
+#pragma unroll
+  for (int j = 0; j < V; j += 4) {
+    const float4 g0 = *reinterpret_cast<const float4*>(g.ss + c + j);
+    const float4 b0 = *reinterpret_cast<const float4*>(g.ss + C + c + j);
+    gam[j] = g0.x; gam[j + 1] = g0.y; gam[j + 2] = g0.z; gam[j + 3] = g0.w;
+    bet[j] = b0.x; bet[j + 1] = b0.y; bet[j + 2] = b0.z; bet[j + 3] = b0.w;
   }
   __syncthreads();
   for (int gi = tid; gi < g.groups; gi += nthr) {  // blocks can be narrower than the group count
@@ -501,9 +529,9 @@ __global__ void __launch_bounds__(256, 2) gn_fir_kernel(const GnFirArgs g) {
     s_rstd[gi] = rsqrtf(var + g.eps);
   }
   __syncthreads();
-  float a[8], bb[8];
+  float a[V], bb[V];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < V; ++j) {
     const int gi = (c + j) / cpg;
     a[j] = s_rstd[gi] * (g.adagn ? (1.f + gam[j]) : gam[j]);
     bb[j] = bet[j] - s_mean[gi] * a[j];
@@ -514,7 +542,6 @@ __global__ void __launch_bounds__(256, 2) gn_fir_kernel(const GnFirArgs g) {
   const __nv_bfloat16* xs = (first ? g.x0 : g.x1) + (long long)b * H * W * Cs + cs;
   __nv_bfloat16* yr = first ? g.y_raw0 : g.y_raw1;
   const int px = blockIdx.x * blockDim.y + threadIdx.y;  // input column (up) / output column (down)
-  const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
   if (UP) {
     if (px >= W) return;
@@ -523,65 +550,58 @@ __global__ void __launch_bounds__(256, 2) gn_fir_kernel(const GnFirArgs g) {
     __nv_bfloat16* ya = g.y_act + (long long)b * 4 * H * W * C + c;
     yr += (long long)b * 4 * H * W * Cs + cs;
     // horizontally filtered row r: L = (x[px-1] + 3 x[px]) / 4, R = (3 x[px] + x[px+1]) / 4, raw and activated
-    float pl[8], pr[8], pal[8], par[8];  // previous row
-    auto hrow = [&](int r, float (&l)[8], float (&rr)[8], float (&al)[8], float (&ar)[8]) {
+    float pl[V], pr[V], pal[V], par[V];  // previous row
+    auto hrow = [&](int r, float (&l)[V], float (&rr)[V], float (&al)[V], float (&ar)[V]) {
       if (r < 0 || r >= H) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) l[j] = rr[j] = al[j] = ar[j] = 0.f;
+        for (int j = 0; j < V; ++j) l[j] = rr[j] = al[j] = ar[j] = 0.f;
         return;
       }
       const __nv_bfloat16* row = xs + ((long long)r * W + px) * Cs;
-      float m[8], c0[8], p[8], am[8], ac[8], ap[8];
-      unpack8(ld_ro16(row), c0);
-      act8(c0, a, bb, ac);
-      if (px > 0) {
-        unpack8(ld_ro16(row - Cs), m);
-        act8(m, a, bb, am);
-      } else {
+      float m[V], c0[V], p[V], am[V], ac[V], ap[V];
+      const bool hm = px > 0, hp = px + 1 < W;
+      ldv<V>(row, c0);
+      if (hm) ldv<V>(row - Cs, m);
+      if (hp) ldv<V>(row + Cs, p);
+      actv<V>(c0, a, bb, ac);
+      if (hm) actv<V>(m, a, bb, am);
+      if (hp) actv<V>(p, a, bb, ap);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = am[j] = 0.f;
-      }
-      if (px + 1 < W) {
-        unpack8(ld_ro16(row + Cs), p);
-        act8(p, a, bb, ap);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) p[j] = ap[j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < V; ++j) {
+        if (!hm) m[j] = am[j] = 0.f;
+        if (!hp) p[j] = ap[j] = 0.f;
         l[j] = 0.25f * m[j] + 0.75f * c0[j];
         rr[j] = 0.75f * c0[j] + 0.25f * p[j];
         al[j] = 0.25f * am[j] + 0.75f * ac[j];
         ar[j] = 0.75f * ac[j] + 0.25f * ap[j];
       }
     };
-    auto emit = [&](int oy, float wp, float wc, const float (&cl)[8], const float (&cr)[8], const float (&cal)[8],
-                    const float (&car)[8]) {
-      float o[8];
+    auto emit = [&](int oy, float wp, float wc, const float (&cl)[V], const float (&cr)[V], const float (&cal)[V],
+                    const float (&car)[V]) {
+      float o[V];
       const long long pix = ((long long)oy * OW + 2 * px);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = wp * pl[j] + wc * cl[j];
-      *reinterpret_cast<uint4*>(yr + pix * Cs) = pack8(o);
+      for (int j = 0; j < V; ++j) o[j] = wp * pl[j] + wc * cl[j];
+      stv<V>(yr + pix * Cs, o);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = wp * pr[j] + wc * cr[j];
-      *reinterpret_cast<uint4*>(yr + (pix + 1) * Cs) = pack8(o);
+      for (int j = 0; j < V; ++j) o[j] = wp * pr[j] + wc * cr[j];
+      stv<V>(yr + (pix + 1) * Cs, o);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = wp * pal[j] + wc * cal[j];
-      *reinterpret_cast<uint4*>(ya + pix * C) = pack8(o);
+      for (int j = 0; j < V; ++j) o[j] = wp * pal[j] + wc * cal[j];
+      stv<V>(ya + pix * C, o);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = wp * par[j] + wc * car[j];
-      *reinterpret_cast<uint4*>(ya + (pix + 1) * C) = pack8(o);
+      for (int j = 0; j < V; ++j) o[j] = wp * par[j] + wc * car[j];
+      stv<V>(ya + (pix + 1) * C, o);
     };
     hrow(r0 - 1, pl, pr, pal, par);
     // step r (r0 .. r1): rows r-1 and r are known -> output rows 2r-1 (if r > r0) and 2r (if r < r1)
     for (int r = r0; r <= r1; ++r) {
-      float cl[8], cr[8], cal[8], car[8];
+      float cl[V], cr[V], cal[V], car[V];
       hrow(r, cl, cr, cal, car);
       if (r > r0) emit(2 * r - 1, 0.75f, 0.25f, cl, cr, cal, car);
       if (r < r1) emit(2 * r, 0.25f, 0.75f, cl, cr, cal, car);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < V; ++j) {
         pl[j] = cl[j];
         pr[j] = cr[j];
         pal[j] = cal[j];
@@ -594,44 +614,64 @@ __global__ void __launch_bounds__(256, 2) gn_fir_kernel(const GnFirArgs g) {
     const int o0 = blockIdx.y * g.strip, o1 = min(OH, o0 + g.strip);
     __nv_bfloat16* ya = g.y_act + (long long)b * OH * OW * C + c;
     yr += (long long)b * OH * OW * Cs + cs;
-    // horizontally filtered row r at output column px: (x[2px-1] + 3 x[2px] + 3 x[2px+1] + x[2px+2]) / 8
-    auto hrow = [&](int r, float (&h)[8], float (&ah)[8]) {
+    const bool hm = px > 0, hp = 2 * px + 2 < W;
+    const __nv_bfloat16* col = xs + (long long)(2 * px) * Cs;
+    // horizontally filtered rows r, r+1 at output column px: (x[2px-1] + 3 x[2px] + 3 x[2px+1] + x[2px+2]) / 8;
+    // all eight loads are issued before any arithmetic
+    auto hrow2 = [&](int r, float (&h)[V], float (&ah)[V], float (&hh)[V], float (&ahh)[V]) {
+      float v[2][4][V];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) h[j] = ah[j] = 0.f;
-      if (r < 0 || r >= H) return;
-      const __nv_bfloat16* row = xs + (long long)r * W * Cs;
+      for (int k = 0; k < 2; ++k) {
+        const bool ok = (r + k >= 0) && (r + k < H);
+        const __nv_bfloat16* row = col + (long long)(r + k) * W * Cs;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int xx = 2 * px - 1 + t;
-        if (xx < 0 || xx >= W) continue;
-        const float w = (t == 0 || t == 3) ? 0.125f : 0.375f;
-        float v[8], av[8];
-        unpack8(ld_ro16(row + (long long)xx * Cs), v);
-        act8(v, a, bb, av);
+        for (int t = 0; t < 4; ++t) {
+          const bool in = ok && (t != 0 || hm) && (t != 3 || hp);
+          if (in) ldv<V>(row + (t - 1) * Cs, v[k][t]);
+          else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          h[j] = fmaf(w, v[j], h[j]);
-          ah[j] = fmaf(w, av[j], ah[j]);
+            for (int j = 0; j < V; ++j) v[k][t][j] = 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const bool ok = (r + k >= 0) && (r + k < H);
+        float (&dh)[V] = k ? hh : h;
+        float (&dah)[V] = k ? ahh : ah;
+#pragma unroll
+        for (int j = 0; j < V; ++j) dh[j] = dah[j] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const bool in = ok && (t != 0 || hm) && (t != 3 || hp);
+          const float w = (t == 0 || t == 3) ? 0.125f : 0.375f;
+          float av[V];
+          if (in) {
+            actv<V>(v[k][t], a, bb, av);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              dh[j] = fmaf(w, v[k][t][j], dh[j]);
+              dah[j] = fmaf(w, av[j], dah[j]);
+            }
+          }
         }
       }
     };
-    float h0[8], ah0[8], h1[8], ah1[8];  // rows 2oy-1 and 2oy
-    hrow(2 * o0 - 1, h0, ah0);
-    hrow(2 * o0, h1, ah1);
+    float h0[V], ah0[V], h1[V], ah1[V];  // rows 2oy-1 and 2oy
+    hrow2(2 * o0 - 1, h0, ah0, h1, ah1);
     for (int oy = o0; oy < o1; ++oy) {
-      float h2[8], ah2[8], h3[8], ah3[8];
-      hrow(2 * oy + 1, h2, ah2);
-      hrow(2 * oy + 2, h3, ah3);
-      float o[8];
+      float h2[V], ah2[V], h3[V], ah3[V];
+      hrow2(2 * oy + 1, h2, ah2, h3, ah3);
+      float o[V];
       const long long pix = (long long)oy * OW + px;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = 0.125f * h0[j] + 0.375f * h1[j] + 0.375f * h2[j] + 0.125f * h3[j];
-      *reinterpret_cast<uint4*>(yr + pix * Cs) = pack8(o);
+      for (int j = 0; j < V; ++j) o[j] = 0.125f * h0[j] + 0.375f * h1[j] + 0.375f * h2[j] + 0.125f * h3[j];
+      stv<V>(yr + pix * Cs, o);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = 0.125f * ah0[j] + 0.375f * ah1[j] + 0.375f * ah2[j] + 0.125f * ah3[j];
-      *reinterpret_cast<uint4*>(ya + pix * C) = pack8(o);
+      for (int j = 0; j < V; ++j) o[j] = 0.125f * ah0[j] + 0.375f * ah1[j] + 0.375f * ah2[j] + 0.125f * ah3[j];
+      stv<V>(ya + pix * C, o);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < V; ++j) {
         h0[j] = h2[j];
         ah0[j] = ah2[j];
         h1[j] = h3[j];
@@ -639,7 +679,6 @@ __global__ void __launch_bounds__(256, 2) gn_fir_kernel(const GnFirArgs g) {
       }
     }
   }
-  (void)z8;
 }
 
 __global__ void nearest_up2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
@@ -888,7 +927,15 @@ extern "C" int evc_gn_fir(const void* x0, int32_t C0, const void* x1, int32_t C1
   g.y_act = reinterpret_cast<__nv_bfloat16*>(y_act);
   g.y_raw0 = reinterpret_cast<__nv_bfloat16*>(y_raw0);
   g.y_raw1 = reinterpret_cast<__nv_bfloat16*>(y_raw1);
-  int pxb = 256 / nvec;
+  // 4 channels per thread (twice the resident warps) wherever the channel count allows a <= 256-wide block row
+  static int vec_env = -1;
+  if (vec_env < 0) {
+    const char* e = getenv("EVC_GN_FIR_VEC");
+    vec_env = e ? atoi(e) : 4;
+  }
+  const int V = (vec_env == 4 && (C % 4) == 0 && (C0 % 4) == 0 && C / 4 <= 256) ? 4 : 8;
+  const int nv = C / V;
+  int pxb = 256 / nv;
   if (pxb < 1) pxb = 1;
   const int cols = up ? W : W / 2, rows = up ? H : H / 2;
   if (pxb > cols) pxb = cols;
@@ -898,9 +945,10 @@ extern "C" int evc_gn_fir(const void* x0, int32_t C0, const void* x1, int32_t C1
   while (strip > 4 && (long long)xb * ((rows + strip - 1) / strip) * B < 4ll * evc_num_sms()) strip >>= 1;
   if (strip > rows) strip = rows;
   g.strip = strip;
-  dim3 grid(xb, (rows + strip - 1) / strip, B), block(nvec, pxb);
-  cudaError_t le = up ? evc_launch(gn_fir_kernel<true>, grid, block, 0, (cudaStream_t)stream, 1, g)
-                      : evc_launch(gn_fir_kernel<false>, grid, block, 0, (cudaStream_t)stream, 1, g);
+  dim3 grid(xb, (rows + strip - 1) / strip, B), block(nv, pxb);
+  void (*kernel)(GnFirArgs) = up ? (V == 4 ? gn_fir_kernel<true, 4> : gn_fir_kernel<true, 8>)
+                                 : (V == 4 ? gn_fir_kernel<false, 4> : gn_fir_kernel<false, 8>);
+  cudaError_t le = evc_launch(kernel, grid, block, 0, (cudaStream_t)stream, 1, g);
   if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
   return evc_check_launch("gn_fir_kernel");
 }
