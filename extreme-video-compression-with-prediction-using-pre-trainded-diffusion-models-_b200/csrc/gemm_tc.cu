@@ -743,11 +743,11 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   // an N tile that splits into two halves of whole 8-row swizzle atoms.
   int cg = 1;
   {
-    const bool can_pair = !p.b_batched && (d->bn % 32) == 0 && d->bn >= 64 && (d->w_rows % d->bn) == 0;
+    const bool can_pair = !p.b_batched && (d->bn % 16) == 0;  // each CTA stages bn/2 rows = whole 8-row swizzle atoms
     if (d->cta_group == 2) {
       if (!can_pair) {
         delete pl;
-        return evc_set_error(EVC_ERR_INVALID, "cta_group 2 needs shared weights, bn % 32 == 0, bn >= 64, N % bn == 0");
+        return evc_set_error(EVC_ERR_INVALID, "cta_group 2 needs shared weights and bn % 16 == 0");
       }
       cg = 2;
     } else if (d->cta_group == 0 && can_pair) {

@@ -73,7 +73,7 @@ class GemmPlan:
         d.max_ctas = max_ctas
         if cta_group is None:
             cta_group = int(os.environ.get("EVC_GEMM_CTA_GROUP", "0"))
-            if cta_group == 2 and (w.dim() == 3 or bn % 32 != 0 or bn < 64 or n % bn != 0):
+            if cta_group == 2 and (w.dim() == 3 or bn % 16 != 0):
                 cta_group = 1  # the env override only applies where pairing is possible
         d.cta_group = cta_group
         if stats is not None:

@@ -103,7 +103,7 @@ typedef struct evc_gemm_desc {
    * (B, stride*H, stride*W, C) and tap (dy,dx) reads input pixel (stride*y + dy, stride*x + dx). */
   int32_t stride;
   /* 0 = automatic, 1 = one CTA per 128-row tile, 2 = CTA pair (tcgen05 cta_group::2, 256-row tile; the pair shares
-   * one B tile, each CTA staging half of it).  2 needs shared weights, bn % 32 == 0, bn >= 64, N % bn == 0. */
+   * one B tile, each CTA staging half of it).  2 needs shared weights (w_batches == 1) and bn % 16 == 0. */
   int32_t cta_group;
   /* Split-precision ("fp32-tolerance") operands, all NULL in the default bf16 mode.  Every bf16 tensor x is then a
    * pair (hi, lo) with hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits); a product is accumulated as

@@ -17,6 +17,9 @@ PAIR_CASES = [
     ("pair_odd_tiles_w8", 5, 8, 8, [(192, 9)], 768, 1, True, False, 1.0, 128),
     ("pair_nin_f32", 2, 32, 32, [(384, 1)], 384, 1, True, False, 1.0, 64),
     ("pair_stride2", 2, 32, 32, [(64, 9)], 128, 0, True, False, 1.0, 128),
+    ("pair_final_conv_n15", 2, 128, 128, [(192, 9)], 15, 1, True, False, 1.0, 16),
+    ("pair_n40_bn48", 3, 32, 32, [(96, 9)], 40, 0, True, False, 1.0, 48),
+    ("pair_ragged_n200_bn64", 3, 16, 16, [(192, 9)], 200, 0, True, True, 1.0, 64),
 ]
 
 

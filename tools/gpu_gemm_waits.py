@@ -16,15 +16,20 @@ DEV = "cuda"
 B = int(os.environ.get("B", "46"))
 
 
-def run(name, H, Cins, N, taps=9, resid=False, stats=False, cg=None, reps=5):
+def run(name, H, Cins, N, taps=9, resid=False, stats=False, cg=None, reps=5, transposed=False):
     segs = [(torch.randn(B, H, H, c, device=DEV).to(torch.bfloat16), taps) for c in Cins]
     K = sum(taps * c for c in Cins)
     w = (torch.randn(N, K, device=DEV) / K ** 0.5).to(torch.bfloat16)
     out = torch.empty(B, H, H, N, device=DEV, dtype=torch.bfloat16)
+    if transposed:  # V^T of the attention blocks: (B, C, H*W), epilogue writes column-major
+        out = torch.empty(B, N, H * H, device=DEV, dtype=torch.bfloat16)
     r = torch.randn(B, H, H, N, device=DEV).to(torch.bfloat16) if resid else None
     st = torch.zeros(B, N, 2, device=DEV, dtype=torch.int64) if stats else None
-    plan = ops.GemmPlan(segs, w, out, 0, out_ld=N, bias=torch.zeros(N, device=DEV), resid=r, resid_ld=N if resid else 0,
-                        alpha=1.0, stats=st, cta_group=cg)
+    if transposed:
+        plan = ops.GemmPlan(segs, w, out, _lib.EVC_OUT_BF16_T, out_ld=H * H, out_bs=N * H * H, bias=torch.zeros(N, device=DEV))
+    else:
+        plan = ops.GemmPlan(segs, w, out, 0, out_ld=N, bias=torch.zeros(N, device=DEV), resid=r, resid_ld=N if resid else 0,
+                            alpha=1.0, stats=st, cta_group=cg)
     for _ in range(2):
         plan.launch()
     torch.cuda.synchronize()
@@ -50,6 +55,18 @@ def run(name, H, Cins, N, taps=9, resid=False, stats=False, cg=None, reps=5):
           f"{100 * v[8] / v[5]:5.1f}%, tcgen05.ld {100 * v[9] / v[5]:5.1f}%, math+stores+stats {100 * v[10] / v[5]:5.1f}%", flush=True)
 
 
+if os.environ.get("SMALLN"):
+    for n in (16, 32, 48):
+        run(f"128^2 192->{n} 3x3 cg1", 128, [192], n, cg=1)
+        run(f"128^2 192->{n} 3x3 cg2", 128, [192], n, cg=2)
+    sys.exit(0)
+if os.environ.get("NIN"):
+    for H, Ch in ((32, 384), (16, 576), (8, 768)):
+        run(f"{H}^2 NIN {Ch}->{Ch} rows", H, [Ch], Ch, taps=1)
+        run(f"{H}^2 NIN {Ch}->{Ch} +resid", H, [Ch], Ch, taps=1, resid=True)
+        run(f"{H}^2 NIN {Ch}->{Ch} transposed", H, [Ch], Ch, taps=1, transposed=True)
+        run(f"{H}^2 NIN {Ch}->{2 * Ch} rows", H, [Ch], 2 * Ch, taps=1)
+    sys.exit(0)
 if os.environ.get("NSWEEP"):
     # does the tensor pipe run faster with a wider N tile?  (shared-memory bandwidth model, profiles/r01_notes.md)
     for n in (64, 96, 128, 192, 256):
