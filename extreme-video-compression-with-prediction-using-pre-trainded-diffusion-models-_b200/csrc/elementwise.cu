@@ -30,17 +30,6 @@ __device__ __forceinline__ float silu_f(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
   return x * r;
 }
-// Two SiLUs with three MUFU ops: one reciprocal of the product (1+e0)(1+e1) serves both (t clamped at -40 so the
-// product stays finite; silu(-40) = -1.7e-16).
-__device__ __forceinline__ void silu_pair(float& x0, float& x1) {
-  float e0, e1, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaxf(x0, -40.f) * -1.4426950408889634f));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaxf(x1, -40.f) * -1.4426950408889634f));
-  const float d0 = 1.f + e0, d1 = 1.f + e1;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d0 * d1));
-  x0 *= r * d1;
-  x1 *= r * d0;
-}
 template <bool SILU, bool PAIR>
 __device__ __forceinline__ uint4 gn_affine_act(const uint4& raw, const float (&a)[8], const float (&bb)[8]) {
   float f[8];

@@ -53,6 +53,13 @@ struct alignas(64) GemmParams {
   CUtensorMap resid_map; // residual as a 2-D tensor (N, B*H*W), 64 x 128 boxes, 128 B swizzle
   int resid_tma;         // 1: the tile's residual rows are fetched by TMA (needs tma_out), 0: cp.async per thread
   int off_resid, off_stat, off_stage;  // byte offsets of the epilogue scratch areas behind the barrier block
+  // fused GroupNorm apply: the epilogue keeps the accumulator in TMEM until every tile of the sample has contributed
+  // its statistics (per-sample ticket), then writes SiLU(GN(acc + bias) * gamma' + beta') instead of the raw value
+  int gn_fuse;
+  const float* gn_ss;   // [gamma' (N) | beta' (N)] of the current label
+  int* gn_ticket;       // [B], zeroed by the caller before the launch
+  float gn_eps, gn_inv_n;
+  int gn_cpg, gn_adagn, tiles_per_sample;
 #ifdef EVC_GEMM_PROF
   int exp_alt;           // timing experiment (wrong results): alternate the accumulator between consecutive MMAs
 #endif
@@ -352,6 +359,76 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     uint8_t* stg_base = tail + p.off_stage + static_cast<uint32_t>(warp - 4) * static_cast<uint32_t>(p.tma_out) * 2048u;
     const uint32_t stg_base_u32 = bar_base + p.off_stage + static_cast<uint32_t>(warp - 4) * static_cast<uint32_t>(p.tma_out) * 2048u;
     int stg_i = 0;
+    // fused GroupNorm apply: two tile-sized slots (bf16, TMA-store layout) replace the per-warp staging buffers
+    uint8_t* stg_base0 = tail + p.off_stage;
+    bool gn_pending = false;
+    int gn_b = 0, gn_n0 = 0;
+    long long gn_pix = 0;
+    auto gn_pass2 = [&](int pb, int pn0, long long ppix, int slot_idx) {
+      if (e == 0) {  // every tile of the sample has added its statistics?
+        int seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.gn_ticket + pb) : "memory");
+          if (seen < p.tiles_per_sample) __nanosleep(32);
+        } while (seen < p.tiles_per_sample);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float2* scoef = reinterpret_cast<float2*>(sstat);  // the statistics scratch is free between tiles
+      for (int j = e; j < p.BN; j += kEpiThreads) {
+        const int c = pn0 + j;
+        float a = 0.f, bb = 0.f;
+        if (c < p.N) {
+          const int g0 = (c / p.gn_cpg) * p.gn_cpg;
+          float s = 0.f, qq = 0.f;
+          for (int k = 0; k < p.gn_cpg; ++k) {
+            const longlong2 st = __ldcg(reinterpret_cast<const longlong2*>(p.stats + ((long long)pb * p.N + g0 + k) * 2));
+            s += (float)((double)st.x * (1.0 / 1048576.0));
+            qq += (float)((double)st.y * (1.0 / 1048576.0));
+          }
+          const float mean = s * p.gn_inv_n;
+          const float var = fmaxf(qq * p.gn_inv_n - mean * mean, 0.f);
+          const float rstd = rsqrtf(var + p.gn_eps);
+          a = rstd * (p.gn_adagn ? 1.f + __ldg(p.gn_ss + c) : __ldg(p.gn_ss + c));
+          bb = __ldg(p.gn_ss + p.N + c) - mean * a;
+        }
+        scoef[j] = make_float2(a, bb);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      uint8_t* slot = stg_base0 + static_cast<uint32_t>(slot_idx) * static_cast<uint32_t>(p.BN) * 256u;
+      const uint32_t slot_u32 = bar_base + p.off_stage + static_cast<uint32_t>(slot_idx) * static_cast<uint32_t>(p.BN) * 256u;
+      const int sw = (lane >> 1) & 3;
+      for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
+        const uint32_t boff = static_cast<uint32_t>((c0 >> 5) * 4 + q) * 2048u;
+        uint8_t* srow = slot + boff + lane * 64;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4* ptr = reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4));
+          const uint4 u = *ptr;
+          float y[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                        bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float2 ab = scoef[c0 + 8 * j + k];
+            y[k] = fmaf(y[k], ab.x, ab.y);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) silu_pair(y[k], y[k + 1]);
+          uint4 o;
+          o.x = pack_bf16x2(y[0], y[1]);
+          o.y = pack_bf16x2(y[2], y[3]);
+          o.z = pack_bf16x2(y[4], y[5]);
+          o.w = pack_bf16x2(y[6], y[7]);
+          *ptr = o;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&p.out_map, slot_u32 + boff, pn0 + c0, static_cast<int>(ppix) + q * 32);
+          bulk_commit();
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // scoef (= sstat) may be overwritten by the next tile's pass 1
+    };
     int it = 0;
     PROF_DECL(long long w_tfull = 0; long long w_pre = 0; long long w_ld = 0; long long w_rest = 0;)
     PROF_T0(t_epi);
@@ -400,6 +477,91 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       if (p.resid_tma) mbar_wait(resid_bar, static_cast<uint32_t>(it) & 1u);
       const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      if (!SPLIT && p.gn_fuse) {
+        // ---- fused GroupNorm apply.  Pass 1 (this tile): bf16(acc + bias) -> this tile's slot in shared memory
+        // (TMA-store layout: [chunk][row quarter][32 rows x 64 B, 64 B swizzle]) + column sums -> statistics + one
+        // ticket for the sample; the accumulator is released at once.  Pass 2 (the PREVIOUS tile, one tile-time
+        // later, when its sample is almost certainly complete): normalise + SiLU in place, TMA stores.  Every warp
+        // only ever touches its own blocks of a slot, so the slots need no cross-warp synchronisation.
+        const bool tile_ok = (b0 < p.B);  // the peer CTA of an odd last pair has no tile
+        const int sw = (lane >> 1) & 3;
+        uint8_t* slot = stg_base0 + static_cast<uint32_t>(it & 1) * static_cast<uint32_t>(p.BN) * 256u;
+        if (lane == 0) bulk_wait_read<0>();  // the stores that read this slot were issued a whole tile ago
+        __syncwarp();
+        for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c0, v);
+          tmem_ld_wait();
+          if (c0 + 64 >= p.BN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+              else mbar_arrive(tempty_bar(acc));
+            }
+          }
+          uint8_t* blk = slot + static_cast<uint32_t>((c0 >> 5) * 4 + q) * 2048u;
+          uint8_t* srow = blk + lane * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b0v = *reinterpret_cast<const float4*>(sbias + c0 + 8 * j);
+            const float4 b1v = *reinterpret_cast<const float4*>(sbias + c0 + 8 * j + 4);
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) + b0v.x, __uint_as_float(v[8 * j + 1]) + b0v.y);
+            u.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) + b0v.z, __uint_as_float(v[8 * j + 3]) + b0v.w);
+            u.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) + b1v.x, __uint_as_float(v[8 * j + 5]) + b1v.y);
+            u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) + b1v.z, __uint_as_float(v[8 * j + 7]) + b1v.w);
+            *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = u;
+          }
+          __syncwarp();
+          const int cp = lane & 15, par = lane >> 4;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          const uint8_t* sb = blk + ((cp & 3) << 2);
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            const int rr = 2 * r + par;
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(sb + rr * 64 + (((cp >> 2) ^ (r & 3)) << 4));
+            const float a0 = bf16_lo(u), a1 = bf16_hi(u);
+            s0 += a0;
+            s1 += a1;
+            q0 = fmaf(a0, a0, q0);
+            q1 = fmaf(a1, a1, q1);
+          }
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+          q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+          if (lane < 16) *reinterpret_cast<float4*>(sstat + (q * p.BN + c0 + 2 * cp) * 2) = make_float4(s0, q0, s1, q1);
+        }
+        if (p.BN <= 32 && grp == 1) {  // this warp had no chunk: it still owes the accumulator release
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+            else mbar_arrive(tempty_bar(acc));
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tile_ok) {
+          for (int i = e; i < 2 * p.BN; i += kEpiThreads) {
+            const int col = i >> 1;
+            if (n0 + col < p.N) {
+              const float t = sstat[i] + sstat[2 * p.BN + i] + sstat[4 * p.BN + i] + sstat[6 * p.BN + i];
+              stat_add(p.stats + ((long long)b0 * p.N + n0 + col) * 2 + (i & 1), t);
+            }
+          }
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (e == 0 && tile_ok)
+          asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p.gn_ticket + b0), "r"(1) : "memory");
+        if (gn_pending) gn_pass2(gn_b, gn_n0, gn_pix, (it & 1) ^ 1);
+        gn_pending = tile_ok;
+        gn_b = b0;
+        gn_n0 = n0;
+        gn_pix = ((long long)b0 * p.H + y0) * p.W + x0;
+        continue;
+      }
       bool released = false;
       for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
         const int ncols = min(32, p.BN - c0);
@@ -642,6 +804,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         }
       }
     }
+    if (!SPLIT && p.gn_fuse && gn_pending) gn_pass2(gn_b, gn_n0, gn_pix, (it & 1) ^ 1);  // `it` = tiles done
     if (p.tma_out != 0 && lane == 0) bulk_wait_all();  // staging buffers are read before the CTA's smem goes away
 #ifdef EVC_GEMM_PROF
     if (e == 0 && rank == 0) {
@@ -902,7 +1065,8 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     if (nbuf > 0) {
       off = (off + 1023) & ~1023;
       p.off_stage = off;
-      off += 8 * nbuf * 2048;
+      // fused GroupNorm apply: two whole-tile slots (bn x 256 B each) instead of the per-warp staging buffers
+      off += (d->gn_ss != nullptr) ? 2 * d->bn * 256 : 8 * nbuf * 2048;
     }
     return off;
   };
@@ -927,6 +1091,26 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     // two staging buffers per epilogue warp unless that would leave fewer than four pipeline stages
     p.tma_out = (tma_env >= 2 && (227 * 1024 - 1024 - layout(2)) / stage_bytes >= 4) ? 2 : 1;
   }
+  p.gn_fuse = 0;
+  if (d->gn_ss != nullptr) {
+    const bool ok = p.tma_out != 0 && d->stats != nullptr && d->gn_ticket != nullptr && d->bias != nullptr &&
+                    d->resid == nullptr && d->alpha == 1.0f && TW * TH == 128 && d->gn_groups > 0 &&
+                    (d->w_rows % d->gn_groups) == 0 && d->max_ctas <= 0;
+    if (!ok) {
+      delete pl;
+      return evc_set_error(EVC_ERR_INVALID,
+                           "fused GroupNorm apply needs stats + ticket + bias, no residual, alpha 1, bf16 rows through the "
+                           "TMA-store epilogue (H*W % 128 == 0, W <= 128, bn % 32 == 0) and N % groups == 0");
+    }
+    p.gn_fuse = 1;
+    p.gn_ss = d->gn_ss;
+    p.gn_ticket = d->gn_ticket;
+    p.gn_eps = d->gn_eps;
+    p.gn_adagn = d->gn_adagn;
+    p.gn_cpg = d->w_rows / d->gn_groups;
+    p.gn_inv_n = 1.0f / ((float)p.gn_cpg * (float)d->H * (float)d->W);
+    p.tiles_per_sample = p.tiles_x * p.tiles_y * p.tiles_n;
+  }
   const int tail_bytes = layout(p.tma_out);
   const int budget = 227 * 1024 - 1024 /*align slack*/ - tail_bytes;
   int stages = budget / stage_bytes;
@@ -949,7 +1133,14 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
 }
 
 extern "C" int evc_gemm_plan_launch(const evc_gemm_plan* pl, const float* bias_override, evc_stream_t stream) {
+  return evc_gemm_plan_launch_gn(pl, bias_override, nullptr, stream);
+}
+
+extern "C" int evc_gemm_plan_launch_gn(const evc_gemm_plan* pl, const float* bias_override, const float* gn_ss_override,
+                                       evc_stream_t stream) {
   if (pl == nullptr) return evc_set_error(EVC_ERR_INVALID, "null plan");
+  if (gn_ss_override != nullptr && !pl->p.gn_fuse)
+    return evc_set_error(EVC_ERR_INVALID, "gn_ss_override on a plan without fused GroupNorm apply");
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaSuccess;
@@ -962,6 +1153,7 @@ extern "C" int evc_gemm_plan_launch(const evc_gemm_plan* pl, const float* bias_o
   }
   GemmParams p = pl->p;
   if (bias_override != nullptr) p.bias = bias_override;
+  if (gn_ss_override != nullptr) p.gn_ss = gn_ss_override;
   cudaError_t e;
   const bool split = pl->split;
   void (*kernel)(GemmParams) = pl->cg == 2 ? (split ? evc_gemm_kernel<2, true> : evc_gemm_kernel<2, false>)

@@ -29,7 +29,9 @@ class GemmDesc(C.Structure):
                 ("out", C.c_void_p), ("out_mode", C.c_int32), ("out_ld", C.c_int64), ("out_bs", C.c_int64),
                 ("bias", C.c_void_p), ("resid", C.c_void_p), ("resid_ld", C.c_int64),
                 ("alpha", C.c_float), ("max_ctas", C.c_int32), ("stats", C.c_void_p), ("stride", C.c_int32), ("cta_group", C.c_int32),
-                ("a_lo", Tensor4 * 3), ("w_lo", C.c_void_p), ("out_lo", C.c_void_p), ("resid_lo", C.c_void_p)]
+                ("a_lo", Tensor4 * 3), ("w_lo", C.c_void_p), ("out_lo", C.c_void_p), ("resid_lo", C.c_void_p),
+                ("gn_ss", C.c_void_p), ("gn_ticket", C.c_void_p), ("gn_eps", C.c_float), ("gn_groups", C.c_int32),
+                ("gn_adagn", C.c_int32)]
 
 
 class AttnDesc(C.Structure):
@@ -60,6 +62,7 @@ SIGNATURES = {
     "evc_set_pdl": (None, [C.c_int]),
     "evc_gemm_plan_create": (C.c_int, [C.POINTER(GemmDesc), C.POINTER(C.c_void_p)]),
     "evc_gemm_plan_launch": (C.c_int, [_vp, _vp, _vp]),
+    "evc_gemm_plan_launch_gn": (C.c_int, [_vp, _vp, _vp, _vp]),
     "evc_gemm_plan_destroy": (None, [_vp]),
     "evc_gemm_plan_flops": (C.c_double, [_vp]),
     "evc_gemm_plan_cta_group": (C.c_int, [_vp]),

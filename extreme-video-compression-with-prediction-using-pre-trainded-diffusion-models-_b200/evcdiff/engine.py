@@ -42,6 +42,15 @@ class Act:
         self.stats = None
 
 
+class _StatSlot:
+    """A slice of the statistics arena that belongs to no activation (fused GroupNorm apply: raw conv statistics and
+    the per-sample tile tickets)."""
+    __slots__ = ("B", "C", "stats")
+
+    def __init__(self, B, C):
+        self.B, self.C, self.stats = B, C, None
+
+
 class Pool:
     """Static scratch reuse: buffers are handed out at plan-build time; stream order makes reuse safe."""
 
@@ -136,6 +145,19 @@ class EngineBase:
         th = max(1, min(H, 128 // tw))
         return (tw * th) % 32 == 0
 
+    def gn_fusable(self, B, H, W, cin_segs, cout):
+        """Can conv -> GroupNorm -> SiLU run as one GEMM launch?  (whole 128-row tiles inside one sample, N tile of
+        whole 32-column chunks; not in split-precision mode)"""
+        if self.split or os.environ.get("EVC_GEMM_FUSE_GN", "1") == "0":
+            return False
+        tw = min(W, 128)
+        th = max(1, min(H, 128 // tw))
+        if tw * th != 128 or W % tw or H % th:
+            return False
+        kblocks = sum(taps * (-(-c // 64)) for c, taps in cin_segs)
+        bn = ops.pick_bn(cout, ops.m_tiles(B, H, W, False), kblocks)
+        return bn % 32 == 0 and bn <= 192  # two bn x 256 B tile slots + >= 3 pipeline stages must fit in 227 KB
+
     def ensure_stats(self, a):
         if a.stats is not None:
             return
@@ -167,7 +189,7 @@ class EngineBase:
         self._op(run, "gn_apply", dict(bytes=out.t.numel() * 4))
 
     def gemm(self, segs, w, out_t, out_mode, out_ld, out_bs=0, bias=None, resid=None, alpha=1.0, bias_fn=None,
-             stats_of=None, stride=1, w_lo=None, out_lo=None, segs_lo=None):
+             stats_of=None, stride=1, w_lo=None, out_lo=None, segs_lo=None, gn=None):
         """One implicit-GEMM launch.  segs: [(Act | tensor (B,H,W,C), taps)].  w: fp32 (N,K) weights (rounded here to bf16,
         or split into a (hi, lo) pair in split-precision mode) or a bf16 per-sample operand (B,N,K) (+ w_lo).
         stats_of: the Act being written; when given (and the tile geometry allows it) its GroupNorm statistics are
@@ -191,7 +213,18 @@ class EngineBase:
         else:
             segs_lo = w_lo = out_lo = resid_lo = None
         stats_t = None
-        if stats_of is not None and out_mode == EVC_OUT_BF16_ROWS and self.can_fuse_stats(stats_of.H, stats_of.W):
+        if gn is not None:
+            # fused GroupNorm apply (see evc_gemm_desc.gn_ss): `out_t` receives act(GN(conv)); the raw statistics and
+            # the tile tickets live in anonymous arena slots.  gn = dict(ss_fn, eps, adagn, groups)
+            assert stats_of is None and not self.split
+            raw = _StatSlot(out_t.shape[0], w.shape[-2])
+            tick = _StatSlot(out_t.shape[0], 1)
+            self.alloc_stats(raw)
+            self.alloc_stats(tick)
+            stats_of = raw
+            stats_t = ("deferred", raw)
+            gn = dict(gn, ticket=tick)
+        elif stats_of is not None and out_mode == EVC_OUT_BF16_ROWS and self.can_fuse_stats(stats_of.H, stats_of.W):
             self.alloc_stats(stats_of)
             stats_t = ("deferred", stats_of)
         plan_args = dict(out_bs=out_bs, bias=bias, resid=resid.t if isinstance(resid, Act) else resid,
@@ -205,7 +238,7 @@ class EngineBase:
         meta = dict(flops=flops, M=M, N=w.shape[-2], K=w.shape[-1], taps=[t for _, t in segs], hw=shp[2] // stride)
         if stats_t is not None:
             # the arena does not exist yet: create the plan in finalize()
-            self._deferred.append((len(self.ops), seg_t, w, out_t, out_mode, out_ld, plan_args, stats_of, bias_fn))
+            self._deferred.append((len(self.ops), seg_t, w, out_t, out_mode, out_ld, plan_args, stats_of, bias_fn, gn))
             self._op(None, "gemm", meta)
             return None
         plan = ops.GemmPlan(seg_t, w, out_t, out_mode, out_ld, **plan_args)
@@ -327,7 +360,17 @@ class EngineBase:
         for a in self._stat_acts:
             _, off, n = a.stats
             a.stats = self.stats_arena[off:off + n]
-        for idx, segs, w, out_t, out_mode, out_ld, plan_args, act, bias_fn in self._deferred:
+        for idx, segs, w, out_t, out_mode, out_ld, plan_args, act, bias_fn, gn in self._deferred:
+            if gn is not None:
+                N = w.shape[-2]
+                dummy = torch.zeros(2 * N, dtype=torch.float32, device=self.device)  # always overridden at launch
+                ticket = gn["ticket"].stats.view(torch.int32)
+                self._keep += [dummy, ticket]
+                plan = ops.GemmPlan(segs, w, out_t, out_mode, out_ld, stats=act.stats,
+                                    gn=dict(ss=dummy, ticket=ticket, eps=gn["eps"], groups=gn["groups"], adagn=gn["adagn"]),
+                                    **plan_args)
+                self.ops[idx] = (lambda li, plan=plan, fn=gn["ss_fn"]: plan.launch(gn_ss=fn(li)))
+                continue
             plan = ops.GemmPlan(segs, w, out_t, out_mode, out_ld, stats=act.stats, **plan_args)
             if bias_fn is None:
                 self.ops[idx] = (lambda li, plan=plan: plan.launch())
@@ -496,13 +539,21 @@ class NCSNppEngine(EngineBase):
             h = h2
             xs = [self.fir(x, s["up"]) for x in xs]
             tmp += xs
-        c0 = self.new_act(h.H, h.W, cout)
-        self.gemm([(h, 9)], pack_conv3(sd[P(i) + ".Conv_0.weight"].to(dev)), c0.t, EVC_OUT_BF16_ROWS, cout,
-                  bias=self.f32(P(i) + ".Conv_0.bias"), stats_of=c0)
-        self.release(h)
-        a1 = self.new_act(c0.H, c0.W, cout)
-        self.gn_apply(c0, None, self._ss(i, 1), 1e-5, True, True, a1)
-        out = self.new_act(c0.H, c0.W, cout, scratch=False)
+        a1 = self.new_act(h.H, h.W, cout)
+        if self.gn_fusable(h.B, h.H, h.W, [(h.C, 9)], cout):
+            # Conv_0 -> GroupNorm_1 -> SiLU in one launch: the raw convolution output never reaches memory
+            c0 = None
+            self.gemm([(h, 9)], pack_conv3(sd[P(i) + ".Conv_0.weight"].to(dev)), a1.t, EVC_OUT_BF16_ROWS, cout,
+                      bias=self.f32(P(i) + ".Conv_0.bias"),
+                      gn=dict(ss_fn=self._ss(i, 1), eps=1e-5, adagn=True, groups=self.fixed_groups or gn_groups(cout)))
+            self.release(h)
+        else:
+            c0 = self.new_act(h.H, h.W, cout)
+            self.gemm([(h, 9)], pack_conv3(sd[P(i) + ".Conv_0.weight"].to(dev)), c0.t, EVC_OUT_BF16_ROWS, cout,
+                      bias=self.f32(P(i) + ".Conv_0.bias"), stats_of=c0)
+            self.release(h)
+            self.gn_apply(c0, None, self._ss(i, 1), 1e-5, True, True, a1)
+        out = self.new_act(a1.H, a1.W, cout, scratch=False)
         w1 = pack_conv3(sd[P(i) + ".Conv_1.weight"].to(dev))
         b1 = sd[P(i) + ".Conv_1.bias"].float()
         if (P(i) + ".Conv_2.weight") in sd:

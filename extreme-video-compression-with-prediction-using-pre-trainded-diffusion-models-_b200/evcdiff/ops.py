@@ -29,7 +29,7 @@ class GemmPlan:
 
     def __init__(self, segs, w, out, out_mode, out_ld, out_bs=0, bias=None, resid=None, resid_ld=0, alpha=1.0,
                  bn=None, max_ctas=0, stats=None, stride=1, cta_group=None, segs_lo=None, w_lo=None, out_lo=None,
-                 resid_lo=None):
+                 resid_lo=None, gn=None):
         lib = load()
         _require_cuda(w, out, bias, resid, *[s[0] for s in segs])
         d = GemmDesc()
@@ -91,7 +91,16 @@ class GemmPlan:
             d.w_lo = w_lo.data_ptr()
             d.out_lo = out_lo.data_ptr() if out_lo is not None else None
             d.resid_lo = resid_lo.data_ptr() if resid_lo is not None else None
-        self._keep = (segs, w, out, bias, resid, stats, segs_lo, w_lo, out_lo, resid_lo)
+        if gn is not None:
+            # fused GroupNorm apply: dict(ss=fp32 [gamma'|beta'] (2N), ticket=int32 (B), eps, groups, adagn)
+            _require_cuda(gn["ss"], gn["ticket"])
+            assert gn["ss"].dtype == torch.float32 and gn["ticket"].dtype == torch.int32 and gn["ticket"].numel() >= B
+            d.gn_ss = gn["ss"].data_ptr()
+            d.gn_ticket = gn["ticket"].data_ptr()
+            d.gn_eps = float(gn["eps"])
+            d.gn_groups = int(gn["groups"])
+            d.gn_adagn = int(bool(gn["adagn"]))
+        self._keep = (segs, w, out, bias, resid, stats, segs_lo, w_lo, out_lo, resid_lo, gn)
         self._lib = lib
         h = C.c_void_p()
         check(lib.evc_gemm_plan_create(C.byref(d), C.byref(h)), "evc_gemm_plan_create")
@@ -99,8 +108,12 @@ class GemmPlan:
         self.flops = lib.evc_gemm_plan_flops(h)
         self.cta_group = lib.evc_gemm_plan_cta_group(h)
 
-    def launch(self, bias_override=None):
-        check(self._lib.evc_gemm_plan_launch(self._h, _ptr(bias_override), stream_ptr()), "evc_gemm_plan_launch")
+    def launch(self, bias_override=None, gn_ss=None):
+        if gn_ss is None:
+            check(self._lib.evc_gemm_plan_launch(self._h, _ptr(bias_override), stream_ptr()), "evc_gemm_plan_launch")
+        else:
+            check(self._lib.evc_gemm_plan_launch_gn(self._h, _ptr(bias_override), _ptr(gn_ss), stream_ptr()),
+                  "evc_gemm_plan_launch_gn")
 
     def __del__(self):
         try:
@@ -170,8 +183,13 @@ def pick_bn(n, mt=None, kblocks=None, sms=148):
     for bn in cands:
         tiles = mt * (n // bn)
         waves = -(-tiles // sms)
-        # cycles: 4 MMAs of bn/2 cycles per 64-wide K block (min 32 each), + pipeline fill + epilogue
-        cost = waves * (kblocks * 4 * max(bn // 2, 32) + 1500 + 12 * bn)
+        # cycles: 4 MMAs per 64-wide K block; measured on B200 (profiles/r01_notes.md) one 128-row UMMA takes
+        # max(154, bn/2 + 62) cycles whatever the CTA grouping (operand delivery, not the bn/2 of the tensor pipe);
+        # + pipeline fill + epilogue
+        if os.environ.get("EVC_PICK_BN_MODEL", "0") == "1":
+            cost = waves * (kblocks * 4 * max(154, bn // 2 + 62) + 1500 + 12 * bn)
+        else:
+            cost = waves * (kblocks * 4 * max(bn // 2, 32) + 1500 + 12 * bn)
         if best_cost is None or cost < best_cost * 0.97:  # prefer wider tiles unless clearly slower
             best, best_cost = bn, cost
     return best

@@ -113,6 +113,20 @@ typedef struct evc_gemm_desc {
   const void* w_lo;
   void* out_lo;
   const void* resid_lo;
+  /* Fused GroupNorm apply (NULL / 0 = off): `out` receives SiLU(GN(acc + bias) * gamma' + beta') instead of the raw
+   * convolution output, i.e. conv -> GroupNorm -> SiLU of ResnetBlockBigGANppGN (layerspp.py:611-613) in one launch,
+   * without the raw tensor ever reaching memory.  The epilogue keeps each accumulator tile in tensor memory until all
+   * tiles of its sample have added their statistics (gn_ticket[b] counts them), then normalises from it.
+   * gn_ss = [gamma' (N) | beta' (N)] fp32, gamma' = 1 + scale when gn_adagn (AdaGN, layerspp.py:520-527); gn_ticket =
+   * B int32 zeroed by the caller before every launch (like stats).  Needs: stats, bias, no residual, alpha = 1, bf16
+   * row output, H*W a multiple of 128 with W <= 128, bn % 32 == 0 (bn <= 192 so that two tile slots fit in shared
+   * memory), N % gn_groups == 0, and one CTA per SM (the grid
+   * is at most the SM count, so every tile of a sample is in flight together). */
+  const float* gn_ss;
+  int32_t* gn_ticket;
+  float gn_eps;
+  int32_t gn_groups;
+  int32_t gn_adagn;
 } evc_gemm_desc;
 
 typedef struct evc_gemm_plan evc_gemm_plan;
@@ -121,6 +135,9 @@ typedef struct evc_gemm_plan evc_gemm_plan;
 int evc_gemm_plan_create(const evc_gemm_desc* desc, evc_gemm_plan** plan);
 /* bias_override: NULL = use desc->bias. Used for per-label bias tables (models/unet.py:87-88). */
 int evc_gemm_plan_launch(const evc_gemm_plan* plan, const float* bias_override, evc_stream_t stream);
+/* same, with the [gamma' | beta'] row of the current label for a plan created with gn_ss (NULL = desc->gn_ss) */
+int evc_gemm_plan_launch_gn(const evc_gemm_plan* plan, const float* bias_override, const float* gn_ss_override,
+                            evc_stream_t stream);
 void evc_gemm_plan_destroy(evc_gemm_plan* plan);
 /* 2 * M * N * K of one launch (dense FLOPs, for the roofline) */
 double evc_gemm_plan_flops(const evc_gemm_plan* plan);

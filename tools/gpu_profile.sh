@@ -1,19 +1,20 @@
 #!/bin/bash
-# ncu evidence for profiles/: launch list (device time per launch) + full captures of the dominant kernels.
-# Same command line plain first (must exit 0), then under ncu.
+# ncu evidence for profiles/: launch list (device time per launch) + full captures of the hot kernels of one UNet
+# evaluation.  Same command line plain first (must exit 0), then under ncu.  The .ncu-rep files are exported to CSV on
+# the box and deleted (gpurun only copies back 64 MiB).
 mkdir -p gpurun_out
+rm -f gpurun_out/*.ncu-rep
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
-$CMD > gpurun_out/plain.log 2> gpurun_out/plain.err &&
+K="regex:evc_gemm_kernel|gn_apply_kernel|gn_fir_kernel"
+$CMD > gpurun_out/plain.log 2> gpurun_out/plain.err || { echo "plain run failed"; tail -5 gpurun_out/plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 520 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:evc_gemm_kernel -s 1 -c 2 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
-echo "gemm capture rc=$?"
-ncu --set full --clock-control none -k regex:evc_gemm_kernel -s 88 -c 14 -o gpurun_out/prof_gemm_up $CMD > gpurun_out/ncu_gemm2.log 2>&1
-echo "gemm (up path) capture rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:gn_apply_kernel -s 2 -c 2 -o gpurun_out/prof_gn_apply $CMD > gpurun_out/ncu_gn.log 2>&1
-echo "gn_apply capture rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:evc_attn_kernel -c 2 -o gpurun_out/prof_attn $CMD > gpurun_out/ncu_attn.log 2>&1
-echo "attn capture rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:fir_up_kernel -s 6 -c 2 -o gpurun_out/prof_fir_up $CMD > gpurun_out/ncu_fir.log 2>&1
-echo "fir capture rc=$?"
-ls -la gpurun_out/ | head -30
+# first 36 hot kernels of the first (eager) evaluation: conv-in, 128x128 down-path convs, gn_apply, gn_fir (down)
+ncu --set full --clock-control none -k "$K" -s 0 -c 36 -o gpurun_out/prof_head $CMD > gpurun_out/ncu_head.log 2>&1
+echo "head capture rc=$?"
+ncu -i gpurun_out/prof_head.ncu-rep --page raw --csv > gpurun_out/ncu_full_head.csv 2>/dev/null; rm -f gpurun_out/prof_head.ncu-rep
+# last 44 hot kernels of that evaluation: 64x64 / 128x128 up-path convs (dominant K=3456 shape), gn_fir (up), final conv
+ncu --set full --clock-control none -k "$K" -s 139 -c 44 -o gpurun_out/prof_tail $CMD > gpurun_out/ncu_tail.log 2>&1
+echo "tail capture rc=$?"
+ncu -i gpurun_out/prof_tail.ncu-rep --page raw --csv > gpurun_out/ncu_full_tail.csv 2>/dev/null; rm -f gpurun_out/prof_tail.ncu-rep
+ls -la gpurun_out/ | head -30; du -sh gpurun_out
