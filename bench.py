@@ -310,10 +310,11 @@ def main():
     achieved = dom[2] / (dom[1] / 1e3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tpath) and dom_key == (753664, 192, 1728):
+    if os.path.exists(tpath):  # DRAM bytes per launch from the committed ncu --set full capture of this shape
         with open(tpath) as f:
-            tj = json.load(f)
-        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            tj = json.load(f).get("shapes", {}).get("x".join(str(v) for v in dom_key))
+        if tj is not None:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     roofline = {"bound": "tensor", "kernel": "evc_gemm_kernel",
                 "launch": f"M={dom_key[0]} N={dom_key[1]} K={dom_key[2]} ({dom[0]} launches per evaluation, "
                           f"{dom[2] / dom[0] / 1e9:.1f} GFLOP each)",
