@@ -367,9 +367,16 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     auto gn_pass2 = [&](int pb, int pn0, long long ppix, int slot_idx) {
       if (e == 0) {  // every tile of the sample has added its statistics?
         int seen;
+        const long long t0 = clock64();
         do {
           asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.gn_ticket + pb) : "memory");
-          if (seen < p.tiles_per_sample) __nanosleep(32);
+          if (seen < p.tiles_per_sample) {
+            __nanosleep(32);
+            // all CTAs of the grid are co-resident (grid <= SM count, one CTA per SM), so the other tiles are always
+            // making progress; a wait of seconds means a caller error (tickets not zeroed, foreign work holding SMs):
+            // fail the launch instead of hanging the device
+            if (clock64() - t0 > (1ll << 33)) __trap();
+          }
         } while (seen < p.tiles_per_sample);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");

@@ -369,7 +369,10 @@ class EngineBase:
                 plan = ops.GemmPlan(segs, w, out_t, out_mode, out_ld, stats=act.stats,
                                     gn=dict(ss=dummy, ticket=ticket, eps=gn["eps"], groups=gn["groups"], adagn=gn["adagn"]),
                                     **plan_args)
-                self.ops[idx] = (lambda li, plan=plan, fn=gn["ss_fn"]: plan.launch(gn_ss=fn(li)))
+                if bias_fn is None:
+                    self.ops[idx] = (lambda li, plan=plan, fn=gn["ss_fn"]: plan.launch(gn_ss=fn(li)))
+                else:
+                    self.ops[idx] = (lambda li, plan=plan, fn=gn["ss_fn"], bf=bias_fn: plan.launch(bf(li), gn_ss=fn(li)))
                 continue
             plan = ops.GemmPlan(segs, w, out_t, out_mode, out_ld, stats=act.stats, **plan_args)
             if bias_fn is None:

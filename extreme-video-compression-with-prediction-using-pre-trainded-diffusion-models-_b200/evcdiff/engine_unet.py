@@ -133,15 +133,23 @@ class PlainUNetEngine(EngineBase):
         ss0 = self._gn_ss(p + ".normalize0")
         h = self.new_act(xa.H, xa.W, cin)
         self.gn_apply(xa, xb, lambda li: ss0, 1e-6, False, True, h)
-        c0 = self.new_act(xa.H, xa.W, cout)
         off, n = self.bias_off[p]
-        self.gemm([(h, 9)], pack_conv3(sd[p + ".conv0.weight"].to(dev)), c0.t, EVC_OUT_BF16_ROWS, cout,
-                  bias=self.dense_b[off:off + n], bias_fn=lambda li, off=off, n=n: self.bias_table[li, off:off + n],
-                  stats_of=c0)
-        self.release(h)
         ss1 = self._gn_ss(p + ".normalize1")
         a1 = self.new_act(xa.H, xa.W, cout)
-        self.gn_apply(c0, None, lambda li: ss1, 1e-6, False, True, a1)
+        bias_fn = lambda li, off=off, n=n: self.bias_table[li, off:off + n]
+        if self.gn_fusable(xa.B, xa.H, xa.W, [(cin, 9)], cout):
+            # conv0 (+ per-label temb bias) -> normalize1 -> Swish in one launch
+            c0 = None
+            self.gemm([(h, 9)], pack_conv3(sd[p + ".conv0.weight"].to(dev)), a1.t, EVC_OUT_BF16_ROWS, cout,
+                      bias=self.dense_b[off:off + n], bias_fn=bias_fn,
+                      gn=dict(ss_fn=lambda li: ss1, eps=1e-6, adagn=False, groups=self.fixed_groups))
+            self.release(h)
+        else:
+            c0 = self.new_act(xa.H, xa.W, cout)
+            self.gemm([(h, 9)], pack_conv3(sd[p + ".conv0.weight"].to(dev)), c0.t, EVC_OUT_BF16_ROWS, cout,
+                      bias=self.dense_b[off:off + n], bias_fn=bias_fn, stats_of=c0)
+            self.release(h)
+            self.gn_apply(c0, None, lambda li: ss1, 1e-6, False, True, a1)
         out = self.new_act(xa.H, xa.W, cout, scratch=False)
         w1 = pack_conv3(sd[p + ".conv1.weight"].to(dev))
         b1 = sd[p + ".conv1.bias"].float()
