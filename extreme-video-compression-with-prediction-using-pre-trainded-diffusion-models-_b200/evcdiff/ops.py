@@ -183,13 +183,9 @@ def pick_bn(n, mt=None, kblocks=None, sms=148):
     for bn in cands:
         tiles = mt * (n // bn)
         waves = -(-tiles // sms)
-        # cycles: 4 MMAs per 64-wide K block; measured on B200 (profiles/r01_notes.md) one 128-row UMMA takes
-        # max(154, bn/2 + 62) cycles whatever the CTA grouping (operand delivery, not the bn/2 of the tensor pipe);
-        # + pipeline fill + epilogue
-        if os.environ.get("EVC_PICK_BN_MODEL", "0") == "1":
-            cost = waves * (kblocks * 4 * max(154, bn // 2 + 62) + 1500 + 12 * bn)
-        else:
-            cost = waves * (kblocks * 4 * max(bn // 2, 32) + 1500 + 12 * bn)
+        # cycles: 4 MMAs of bn/2 cycles per 64-wide K block (min 32 each), + pipeline fill + epilogue.  (The measured
+        # cost of a 128-row UMMA is max(154, bn/2 + 62) cycles, profiles/r01_notes.md; using it picks the same tiles.)
+        cost = waves * (kblocks * 4 * max(bn // 2, 32) + 1500 + 12 * bn)
         if best_cost is None or cost < best_cost * 0.97:  # prefer wider tiles unless clearly slower
             best, best_cost = bn, cost
     return best
