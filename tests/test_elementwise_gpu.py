@@ -216,3 +216,63 @@ def test_sampler_updates_match_oracle_arithmetic():
     got = pndm._combine(es, (55.0, -59.0, 37.0, -9.0), 1 / 24)
     torch.cuda.synchronize()
     assert common.rel_l2(got, ref) < 1e-6
+
+
+def _guarded(shape, dtype, fill):
+    """A tensor placed in the middle of a larger allocation; returns (view, check) where check() asserts the guard
+    bands are untouched (compute-sanitizer is not available on the GPU pool, so out-of-bounds stores are caught here)."""
+    n = int(torch.tensor(shape).prod())
+    pad = 4096
+    buf = torch.full((n + 2 * pad,), fill, device=DEV, dtype=dtype)
+    view = buf[pad:pad + n].view(*shape)
+
+    def check():
+        lo, hi = buf[:pad], buf[pad + n:]
+        ok = (lo != lo).all() and (hi != hi).all() if fill != fill else bool((lo == fill).all() and (hi == fill).all())
+        assert bool(ok), "store outside the output tensor"
+    return view, check
+
+
+@pytest.mark.parametrize("B,H,C0,C1,up", [(2, 16, 192, 0, True), (3, 16, 192, 96, False), (2, 6, 64, 0, True), (1, 10, 96, 32, False)])
+def test_gn_fir_stays_inside_its_outputs(B, H, C0, C1, up):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(9)
+    C = C0 + C1
+    x0 = nhwc(torch.randn(B, C0, H, H, device=DEV, generator=g))
+    x1 = nhwc(torch.randn(B, C1, H, H, device=DEV, generator=g)) if C1 else None
+    ss = torch.randn(2 * C, device=DEV, generator=g) * 0.3
+    st0 = torch.zeros(B, C0, 2, device=DEV, dtype=torch.int64)
+    ops.gn_stats(x0, B, H * H, C0, st0)
+    st1 = None
+    if C1:
+        st1 = torch.zeros(B, C1, 2, device=DEV, dtype=torch.int64)
+        ops.gn_stats(x1, B, H * H, C1, st1)
+    H2 = 2 * H if up else H // 2
+    nan = float("nan")
+    ya, ca = _guarded((B, H2, H2, C), torch.bfloat16, nan)
+    r0, c0 = _guarded((B, H2, H2, C0), torch.bfloat16, nan)
+    r1, c1 = _guarded((B, H2, H2, C1), torch.bfloat16, nan) if C1 else (None, None)
+    ops.gn_fir(x0, C0, x1, C1, B, H, H, st0, st1, O.gn_groups(C), 1e-5, ss, True, up, ya, r0, r1)
+    torch.cuda.synchronize()
+    for t, chk in ((ya, ca), (r0, c0), (r1, c1)):
+        if t is not None:
+            assert torch.isfinite(t.float()).all()
+            chk()
+
+
+def test_gn_apply_stays_inside_its_output():
+    ops = _ops()
+    B, H, C0, C1 = 3, 10, 96, 32
+    g = torch.Generator(device=DEV).manual_seed(10)
+    x0 = nhwc(torch.randn(B, C0, H, H, device=DEV, generator=g))
+    x1 = nhwc(torch.randn(B, C1, H, H, device=DEV, generator=g))
+    ss = torch.randn(2 * (C0 + C1), device=DEV, generator=g) * 0.3
+    st0 = torch.zeros(B, C0, 2, device=DEV, dtype=torch.int64)
+    st1 = torch.zeros(B, C1, 2, device=DEV, dtype=torch.int64)
+    ops.gn_stats(x0, B, H * H, C0, st0)
+    ops.gn_stats(x1, B, H * H, C1, st1)
+    y, chk = _guarded((B, H, H, C0 + C1), torch.bfloat16, float("nan"))
+    ops.gn_apply(x0, C0, x1, C1, B, H * H, st0, st1, O.gn_groups(C0 + C1), 1e-5, ss, True, True, y)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y.float()).all()
+    chk()

@@ -187,3 +187,33 @@ def test_gemm_fused_groupnorm_apply(B, H, Cin, N, bn, cg):
     assert rel_l2(got, ref) < 5e-3, rel_l2(got, ref)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     assert int(ticket.min()) == int(ticket.max()) == (H * H // 128) * (N // bn)
+
+
+def test_gemm_fused_groupnorm_guard_bands():
+    """The fused GroupNorm-apply epilogue writes only `out`, `stats` and `gn_ticket` (guard bands around all three;
+    an odd number of 128-row tiles, so the second CTA of the last pair has no tile)."""
+    ops = _setup()
+    B, H, Cin, N = 3, 16, 64, 192  # 6 tiles -> 3 pairs; B = 3 with 2 tiles per sample
+    g = torch.Generator(device="cuda").manual_seed(77)
+    a = torch.randn(B, H, H, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, 9 * Cin, device="cuda", generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    ss = torch.randn(2 * N, device="cuda", generator=g) * 0.3
+    pad = 1024
+    obuf = torch.full((B * H * H * N + 2 * pad,), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out = obuf[pad:pad + B * H * H * N].view(B, H, H, N)
+    sbuf = torch.zeros(B * N * 2 + 2 * pad, device="cuda", dtype=torch.int64)
+    stats = sbuf[pad:pad + B * N * 2].view(B, N, 2)
+    tbuf = torch.zeros(B + 2 * pad, device="cuda", dtype=torch.int32)
+    ticket = tbuf[pad:pad + B]
+    for cg in (1, 2):
+        obuf.fill_(float("nan")); sbuf.zero_(); tbuf.zero_()
+        plan = ops.GemmPlan([(a, 9)], w, out, 0, out_ld=N, bias=bias, bn=192, stats=stats, cta_group=cg,
+                            gn=dict(ss=ss, ticket=ticket, eps=1e-5, groups=32, adagn=True))
+        plan.launch()
+        torch.cuda.synchronize()
+        assert torch.isfinite(out.float()).all()
+        assert bool(torch.isnan(obuf[:pad].float()).all()) and bool(torch.isnan(obuf[pad + B * H * H * N:].float()).all())
+        assert int(sbuf[:pad].abs().sum()) == 0 and int(sbuf[pad + B * N * 2:].abs().sum()) == 0
+        assert int(tbuf[:pad].abs().sum()) == 0 and int(tbuf[pad + B:].abs().sum()) == 0
+        assert ticket.tolist() == [2, 2, 2]
