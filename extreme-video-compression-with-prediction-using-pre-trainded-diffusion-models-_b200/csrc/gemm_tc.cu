@@ -1,15 +1,21 @@
 // Implicit-GEMM convolution / batched GEMM on the sm_100a tensor cores.
 //
 // One persistent, warp-specialised kernel: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer,
-// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> global).
+// warp 2 = TMEM allocator, warps 4..11 = epilogue.
 //   * A operand: NHWC bf16 activations fetched by 4-D TMA boxes (64 channels x TW x TH x TB pixels = one
 //     128 x 64 K-major SWIZZLE_128B tile).  A 3x3 convolution is nine shifted boxes; TMA out-of-bounds
 //     zero fill implements the zero padding, so no im2col buffer ever exists in HBM.
 //   * B operand: packed bf16 weights (N, K_total) fetched by 3-D TMA boxes (64 x BN x 1).
 //   * accumulators: fp32 in TMEM, two stages of 256 columns so the epilogue of tile i overlaps the main
 //     loop of tile i+1.
+//   * epilogue, bf16 row outputs of whole 128-row tiles (every layer of the models): TMEM -> registers -> +bias
+//     +residual (fetched by TMA) -> bf16 -> 64 B-swizzled 32 x 32 blocks in shared memory -> TMA stores; the fused
+//     GroupNorm statistics are column sums read back from those blocks; with gn_ss the whole tile is parked in a
+//     shared-memory slot and normalised + activated one tile later, once its sample's statistics are complete.
+//     Other outputs (fp32, transposed, ragged toy shapes, split precision): registers -> global per thread.
 // Replaces cuDNN conv2d / cuBLAS einsum of the reference (models/better/layers.py:89-113, 521-544;
-// models/better/layerspp.py:239-243; models/unet.py:49-63, 114-119).
+// models/better/layerspp.py:239-243; models/unet.py:49-63, 114-119) and, fused, the GroupNorm reduction and the
+// AdaGN + SiLU pass after Conv_0 (models/better/layerspp.py:520-527, 611-613).
 #include <stdlib.h>
 
 #include "evc_host.h"

@@ -9,11 +9,11 @@ K="regex:evc_gemm_kernel|gn_apply_kernel|gn_fir_kernel"
 $CMD > gpurun_out/plain.log 2> gpurun_out/plain.err || { echo "plain run failed"; tail -5 gpurun_out/plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 520 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
-# first 36 hot kernels of the first (eager) evaluation: conv-in, 128x128 down-path convs, gn_apply, gn_fir (down)
+# 36 + 44 hot kernels from the eager warm-up evaluations (both windows together cover every launch shape of the
+# 128x128 and 64x64 levels, including the dominant K=3456 convolution, gn_fir up and down, and the output conv)
 ncu --set full --clock-control none -k "$K" -s 0 -c 36 -o gpurun_out/prof_head $CMD > gpurun_out/ncu_head.log 2>&1
 echo "head capture rc=$?"
 ncu -i gpurun_out/prof_head.ncu-rep --page raw --csv > gpurun_out/ncu_full_head.csv 2>/dev/null; rm -f gpurun_out/prof_head.ncu-rep
-# last 44 hot kernels of that evaluation: 64x64 / 128x128 up-path convs (dominant K=3456 shape), gn_fir (up), final conv
 ncu --set full --clock-control none -k "$K" -s 139 -c 44 -o gpurun_out/prof_tail $CMD > gpurun_out/ncu_tail.log 2>&1
 echo "tail capture rc=$?"
 ncu -i gpurun_out/prof_tail.ncu-rep --page raw --csv > gpurun_out/ncu_full_tail.csv 2>/dev/null; rm -f gpurun_out/prof_tail.ncu-rep
