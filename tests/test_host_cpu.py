@@ -162,3 +162,22 @@ def test_pipeline_get_model_loads_checkpoint_once():
     cfg.model.ema = False
     net = get_model(cfg, states=states)
     assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), src.state_dict().values()))
+
+
+def test_tile_planning_host_logic():
+    """Host-side mirrors of the kernel's tiling (ops.m_tiles / ops.pick_bn) and the engine's fusion rules."""
+    from evcdiff import ops
+    from evcdiff.engine import EngineBase
+    # 128-row M tiles: one image row at 128x128, whole small images batched into a tile at 8x8
+    assert ops.m_tiles(46, 128, 128, False) == 46 * 128
+    assert ops.m_tiles(46, 64, 64, False) == 46 * 32
+    assert ops.m_tiles(46, 8, 8, False) == 23 and ops.m_tiles(5, 8, 8, False) == 3
+    assert ops.m_tiles(4, 8, 8, True) == 4  # per-sample B operand: never two samples in a tile
+    # large problems take the widest tile that divides N; N = 15 falls back to a padded 16-wide tile
+    assert ops.pick_bn(192, ops.m_tiles(46, 128, 128, False), 27) == 192
+    assert ops.pick_bn(15) == 16 and ops.pick_bn(768) == 256
+    for n in (192, 384, 576, 768, 1152, 1536):
+        bn = ops.pick_bn(n, ops.m_tiles(46, 8, 8, False), 108)
+        assert n % bn == 0 and bn % 16 == 0
+    # fused statistics need whole 32-row warp slices inside one sample; the fused GroupNorm apply whole 128-row tiles
+    assert EngineBase.can_fuse_stats(128, 128) and EngineBase.can_fuse_stats(8, 8) and not EngineBase.can_fuse_stats(2, 2)
