@@ -1058,7 +1058,7 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   const long long m_total = (long long)d->B * d->H * d->W;
   const bool can_tma_out = tma_env > 0 && !split && d->out_mode == EVC_OUT_BF16_ROWS && p.rows_valid == 128 &&
                            (d->bn % 32) == 0 && (d->out_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 &&
-                           m_total < (1ll << 31);
+                           m_total < (1ll << 31) - 256;  // pixel coordinates of the TMA maps are 32-bit, incl. the tile of an odd last pair
   p.resid_tma = (can_tma_out && rtma_env > 0 && d->resid != nullptr && (d->resid_ld % 8) == 0 &&
                  (reinterpret_cast<uintptr_t>(d->resid) & 15) == 0) ? 1 : 0;
   if (p.resid_tma) p.resid_smem = 0;
