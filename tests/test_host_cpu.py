@@ -181,3 +181,21 @@ def test_tile_planning_host_logic():
         assert n % bn == 0 and bn % 16 == 0
     # fused statistics need whole 32-row warp slices inside one sample; the fused GroupNorm apply whole 128-row tiles
     assert EngineBase.can_fuse_stats(128, 128) and EngineBase.can_fuse_stats(8, 8) and not EngineBase.can_fuse_stats(2, 2)
+
+
+def test_header_is_valid_c_and_links_from_a_c_host(tmp_path):
+    """include/evcdiff.h is the drop-in boundary for non-Python hosts: it must compile as C99 with warnings as errors,
+    link against libevcdiff.so, and agree with the library on struct sizes (examples/c_abi_demo.c, CPU part only)."""
+    import shutil
+    import subprocess
+    from evcdiff import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    _lib.load()
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "c_abi_demo")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", libdir, "-levcdiff",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "evcdiff ABI version 1" in out
