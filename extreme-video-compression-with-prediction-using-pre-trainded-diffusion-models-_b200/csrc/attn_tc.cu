@@ -36,7 +36,8 @@ struct alignas(64) AttnParams {
 __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp-uniform warp index (see gemm_tc.cu): the producer / MMA warps run convergent loops, one elected lane issues
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
   const int d = p.d, kc_n = d / 64;
   const int T = p.N / kBK;  // key tiles (N % 64 == 0; a 64-query sample uses half of the 128-row tile, TMA zero-fills the rest)
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
   const uint32_t tmem_S = tmem_base;         // 2 x 64 columns
   const uint32_t tmem_O = tmem_base + 128u;  // d columns
 
@@ -91,25 +93,35 @@ __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_
   const int cq = head * d;          // channel offset of this head's q
   const int ck = p.C + head * d;    // ... and k inside the fused [q | k] rows
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    mbar_expect_tx(q_full, q_bytes);
-    for (int kc = 0; kc < kc_n; ++kc) tma_load_3d(&p.q_map, sQ + kc * (kBQ * 128u), q_full, cq + kc * 64, q0, b);
+    if (elect_one()) {
+      mbar_expect_tx(q_full, q_bytes);
+      for (int kc = 0; kc < kc_n; ++kc) tma_load_3d(&p.q_map, sQ + kc * (kBQ * 128u), q_full, cq + kc * 64, q0, b);
+    }
+    __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
     auto load_k = [&](int j) {
       mbar_wait(kv_empty(stage), phase ^ 1u);
-      mbar_expect_tx(kv_full(stage), st_bytes);
       const uint32_t dst = sRing + stage * st_bytes;
-      for (int kc = 0; kc < kc_n; ++kc) tma_load_3d(&p.k_map, dst + kc * (kBK * 128u), kv_full(stage), ck + kc * 64, j * kBK, b);
+      if (elect_one()) {
+        mbar_expect_tx(kv_full(stage), st_bytes);
+        for (int kc = 0; kc < kc_n; ++kc)
+          tma_load_3d(&p.k_map, dst + kc * (kBK * 128u), kv_full(stage), ck + kc * 64, j * kBK, b);
+      }
+      __syncwarp();
       if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
     };
     auto load_v = [&](int j) {
       mbar_wait(kv_empty(stage), phase ^ 1u);
-      mbar_expect_tx(kv_full(stage), st_bytes);
       const uint32_t dst = sRing + stage * st_bytes;
-      for (int dc = 0; dc < p.n_dchunks; ++dc)
-        tma_load_3d(&p.v_map, dst + dc * (p.dv_box * 128u), kv_full(stage), j * kBK, head * d + dc * p.dv_box, b);
+      if (elect_one()) {
+        mbar_expect_tx(kv_full(stage), st_bytes);
+        for (int dc = 0; dc < p.n_dchunks; ++dc)
+          tma_load_3d(&p.v_map, dst + dc * (p.dv_box * 128u), kv_full(stage), j * kBK, head * d + dc * p.dv_box, b);
+      }
+      __syncwarp();
       if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
     };
     for (int j = 0; j < T; ++j) load_k(j);  // pass 1
@@ -118,8 +130,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_
       if (j + 1 < T) load_k(j + 1);
       load_v(j);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one elected lane, always the same)
     const uint32_t idesc_s = umma_idesc_bf16(128u, kBK);
     const uint32_t idesc_o = umma_idesc_bf16(128u, static_cast<uint32_t>(p.dv_box));
     int stage = 0;
@@ -130,15 +142,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_
       mbar_wait(s_empty(t & 1), ((t >> 1) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t kt = sRing + stage * st_bytes;
-      for (int kc = 0; kc < kc_n; ++kc) {
-        const uint64_t da = umma_desc_sw128(sQ + kc * (kBQ * 128u));
-        const uint64_t db = umma_desc_sw128(kt + kc * (kBK * 128u));
+      if (elect_one()) {
+        for (int kc = 0; kc < kc_n; ++kc) {
+          const uint64_t da = umma_desc_sw128(sQ + kc * (kBQ * 128u));
+          const uint64_t db = umma_desc_sw128(kt + kc * (kBK * 128u));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_S + (t & 1) * kBK, da + 2u * k, db + 2u * k, idesc_s, (kc | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_S + (t & 1) * kBK, da + 2u * k, db + 2u * k, idesc_s, (kc | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(kv_empty(stage));
+        umma_commit(s_full(t & 1));
       }
-      umma_commit(kv_empty(stage));
-      umma_commit(s_full(t & 1));
+      __syncwarp();
       if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
       ++t;
     };
@@ -152,17 +167,20 @@ __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_
       tc_fence_after();
       const uint32_t vt = sRing + stage * st_bytes;
       const uint64_t da = umma_desc_sw128(sP + (j & 1) * (kBQ * kBK * 2u));
-      for (int dc = 0; dc < p.n_dchunks; ++dc) {
-        const uint64_t db = umma_desc_sw128(vt + dc * (p.dv_box * 128u));
+      if (elect_one()) {
+        for (int dc = 0; dc < p.n_dchunks; ++dc) {
+          const uint64_t db = umma_desc_sw128(vt + dc * (p.dv_box * 128u));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_O + dc * p.dv_box, da + 2u * k, db + 2u * k, idesc_o, (j | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_O + dc * p.dv_box, da + 2u * k, db + 2u * k, idesc_o, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(kv_empty(stage));
+        umma_commit(p_empty(j & 1));
+        if (j + 1 == T) umma_commit(o_full);
       }
-      umma_commit(kv_empty(stage));
-      umma_commit(p_empty(j & 1));
+      __syncwarp();
       if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
     }
-    umma_commit(o_full);
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax / epilogue (thread = query row)
     const int q = warp & 3;

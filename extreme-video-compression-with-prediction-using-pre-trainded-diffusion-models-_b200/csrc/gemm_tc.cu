@@ -189,7 +189,10 @@ template <int CG, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, so the producer / MMA loops below are
+  // convergent code whose descriptors live in uniform registers (a `lane == 0` loop makes ptxas wrap every
+  // UTMALDG / UTCHMMA / UTCBAR in an ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall loop)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;  // 0 = leader (issues the MMAs)
   const int unit = blockIdx.x / CG;
@@ -232,14 +235,16 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);  // warp-uniform for the compiler
 
   const int m_pairs = (p.m_tiles + CG - 1) / CG;
   const int total_tiles = m_pairs * p.tiles_n;
   pdl_wait();     // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
   pdl_trigger();
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp walks the loop, one
+    // elected lane issues)
     int stage = 0;
     uint32_t phase = 0;
     PROF_DECL(long long w_empty = 0;)
@@ -262,17 +267,20 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
             mbar_wait(empty_bar(stage), phase ^ 1u);
             PROF_ADD(w_empty, t_e);
             const uint32_t sa = base + stage * stage_bytes;
-            if (CG == 2) {
-              // both CTAs' bytes land on the leader's barrier; the peer contributes a plain (remote) arrival
-              if (rank == 0) mbar_expect_tx(full_bar(stage), p.tx_bytes * 2u);
-              else mbar_arrive_cluster(full_bar(stage), 0);
-              tma_load_4d_2sm(am, sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
-              tma_load_3d_2sm(bm, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
-            } else {
-              mbar_expect_tx(full_bar(stage), p.tx_bytes);
-              tma_load_4d(am, sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
-              tma_load_3d(bm, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
+            if (elect_one()) {
+              if (CG == 2) {
+                // both CTAs' bytes land on the leader's barrier; the peer contributes a plain (remote) arrival
+                if (rank == 0) mbar_expect_tx(full_bar(stage), p.tx_bytes * 2u);
+                else mbar_arrive_cluster(full_bar(stage), 0);
+                tma_load_4d_2sm(am, sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
+                tma_load_3d_2sm(bm, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
+              } else {
+                mbar_expect_tx(full_bar(stage), p.tx_bytes);
+                tma_load_4d(am, sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
+                tma_load_3d(bm, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
+              }
             }
+            __syncwarp();
             if (++stage == p.num_stages) {
               stage = 0;
               phase ^= 1u;
@@ -283,10 +291,13 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     }
     PROF_DECL(long long tot_prod = 0;)
     PROF_ADD(tot_prod, t_prod);
-    PROF_OUT(3, tot_prod);
-    PROF_OUT(4, w_empty);
-  } else if (warp == 1 && lane == 0 && rank == 0) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0) {
+      PROF_OUT(3, tot_prod);
+      PROF_OUT(4, w_empty);
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only; whole warp walks
+    // the loop with warp-uniform descriptors, one elected lane -- always the same one -- issues MMAs and commits)
     const uint32_t idesc = umma_idesc_bf16(128u * CG, static_cast<uint32_t>(p.BN));
     int stage = 0;
     uint32_t phase = 0;
@@ -309,24 +320,27 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         const uint32_t sa = base + stage * stage_bytes;
         const uint64_t da = umma_desc_sw128(sa);
         const uint64_t db = umma_desc_sw128(sa + kABytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+          for (int k = 0; k < 4; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
 #ifdef EVC_GEMM_PROF
-          const uint32_t td = tmem_d ^ ((p.exp_alt && (k & 1)) ? static_cast<uint32_t>(kAccStride) : 0u);
+            const uint32_t td = tmem_d ^ ((p.exp_alt && (k & 1)) ? static_cast<uint32_t>(kAccStride) : 0u);
 #else
-          const uint32_t td = tmem_d;
+            const uint32_t td = tmem_d;
 #endif
-          if (CG == 2) umma_bf16_2sm(td, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          else umma_bf16(td, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_bf16_2sm(td, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(td, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if (CG == 2) {
+            umma_commit_2sm(empty_bar(stage), 3);  // frees this stage in both CTAs
+            if (kb == p.total_kb - 1) umma_commit_2sm(tfull_bar(acc), 3);
+          } else {
+            umma_commit(empty_bar(stage));
+            if (kb == p.total_kb - 1) umma_commit(tfull_bar(acc));
+          }
         }
-        if (CG == 2) {
-          umma_commit_2sm(empty_bar(stage), 3);  // frees this stage in both CTAs
-          if (kb == p.total_kb - 1) umma_commit_2sm(tfull_bar(acc), 3);
-        } else {
-          umma_commit(empty_bar(stage));
-          if (kb == p.total_kb - 1) umma_commit(tfull_bar(acc));
-        }
+        __syncwarp();
         if (++stage == p.num_stages) {
           stage = 0;
           phase ^= 1u;
@@ -335,10 +349,12 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     }
     PROF_DECL(long long tot_mma = 0;)
     PROF_ADD(tot_mma, t_mma);
-    PROF_OUT(0, tot_mma);
-    PROF_OUT(1, w_full);
-    PROF_OUT(2, w_tempty);
-    PROF_OUT(7, 1);
+    if (lane == 0) {
+      PROF_OUT(0, tot_mma);
+      PROF_OUT(1, w_full);
+      PROF_OUT(2, w_tempty);
+      PROF_OUT(7, 1);
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     // Per tile: (1) while the main loop of this tile is still running, stage the bias slice in smem and
@@ -435,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           tma_store_2d(&p.out_map, slot_u32 + boff, pn0 + c0, static_cast<int>(ppix) + q * 32);
           bulk_commit();
         }
@@ -463,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         for (int j = e; j < p.BN; j += kEpiThreads) sbias[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
       }
       if (p.resid_tma) {
-        if (e == 0) {
+        if (warp == 4 && elect_one()) {
           const int panels = (p.BN + 63) >> 6;
           const long long tile_pix = ((long long)b0 * p.H + y0) * p.W + x0;
           mbar_expect_tx(resid_bar, static_cast<uint32_t>(panels) * 16384u);
@@ -499,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         const bool tile_ok = (b0 < p.B);  // the peer CTA of an odd last pair has no tile
         const int sw = (lane >> 1) & 3;
         uint8_t* slot = stg_base0 + static_cast<uint32_t>(it & 1) * static_cast<uint32_t>(p.BN) * 256u;
-        if (lane == 0) bulk_wait_read<0>();  // the stores that read this slot were issued a whole tile ago
+        if (elect_one()) bulk_wait_read<0>();  // the stores that read this slot were issued a whole tile ago
         __syncwarp();
         for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
           uint32_t v[32];
@@ -652,7 +668,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           }
           const uint32_t boff = (p.tma_out == 2 ? static_cast<uint32_t>(stg_i & 1) : 0u) * 2048u;
           ++stg_i;
-          if (lane == 0) {  // the TMA unit must have finished reading this buffer (store issued two / one chunks ago)
+          if (elect_one()) {  // the TMA unit must have finished reading this buffer (store issued two / one chunks ago)
             if (p.tma_out == 2) bulk_wait_read<1>();
             else bulk_wait_read<0>();
           }
@@ -670,7 +686,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {  // always the same lane: bulk groups are per thread
             const long long tile_pix = ((long long)b0 * p.H + y0) * p.W + x0;  // tile rows are consecutive pixels
             tma_store_2d(&p.out_map, stg_base_u32 + boff, n, static_cast<int>(tile_pix) + q * 32);
             bulk_commit();
@@ -818,7 +834,8 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       }
     }
     if (!SPLIT && p.gn_fuse && gn_pending) gn_pass2(gn_b, gn_n0, gn_pix, (it & 1) ^ 1);  // `it` = tiles done
-    if (p.tma_out != 0 && lane == 0) bulk_wait_all();  // staging buffers are read before the CTA's smem goes away
+    __syncwarp();
+    if (p.tma_out != 0 && elect_one()) bulk_wait_all();  // staging buffers are read before the CTA's smem goes away
 #ifdef EVC_GEMM_PROF
     if (e == 0 && rank == 0) {
       long long tot_epi = 0;
