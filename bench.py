@@ -2,14 +2,16 @@
 """bench.py -- predicted frames/s of the conditional video-diffusion sampling path (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            our B200 path (default N=1)
-    python bench.py --impl reference --steps K --warmup W    reference CPU implementation (oracle port), rank 0 only
+    python bench.py --impl reference --steps K --warmup W    the reference's own CPU path (rank 0 only)
     torchrun ... bench.py --gpus N ...                       one rank per GPU, videos sharded, one NCCL gather per step
 
 Workload (config.workload): BASELINE.json configs[1] -- the city_bonn.npy-shaped set of 46 videos (synthetic
 stand-in, city_bonn.npy is not shipped), 100-step DDPM (101 UNet evaluations) with the random-init NCSN++ UNet of
-configs/mine.yml; one "step" = one sampling cycle = 5 predicted 128x128 frames for every video of the rank's
-shard.  Weak scaling: every rank holds its own 46-video set (no collective inside the loop; one NCCL gather of
-the predicted frames per step).  One JSON line on stdout (rank 0).
+configs/mine.yml; one "step" = one sampling cycle = 5 predicted 128x128 frames for every video.  Strong scaling
+(default): the 46 videos are sharded by video over the N ranks (6/6/6/6/6/6/5/5 at N=8), every rank samples its
+shard with its slice of the global-batch noise (no collective inside the loop), one NCCL gather of the predicted
+frames per step; `--scaling weak` gives every rank its own 46-video set.  BASELINE configs[2]:
+`--videos 512 --sampler fpndm --subsample 20`.  One JSON line on stdout (rank 0).
 """
 import argparse
 import json
@@ -97,11 +99,54 @@ class ClockSampler:
 
 
 _CPU_SD = None
+REF_ROOTS = [os.environ.get("EVC_REF"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"]
 
 
-def cpu_reference_fps(n_evals, threads):
-    """Reference CPU path (oracle port of models/__init__.py ddpm_sampler + NCSN++ fp32) on the host cores:
-    B=1, `n_evals` UNet evaluations + sampler updates timed, extrapolated to the 101 of a DDPM-100 cycle."""
+def find_reference():
+    """Root of an importable copy of the UNMODIFIED reference (its models/ package), or None."""
+    for r in REF_ROOTS:
+        if r and os.path.isfile(os.path.join(r, "models", "__init__.py")) and \
+                os.path.isfile(os.path.join(r, "models", "better", "ncsnpp_more.py")):
+            return r
+    return None
+
+
+_REF_NET = None
+
+
+def reference_cpu_fps(n_steps, threads):
+    """The reference's own CPU path: models.ddpm_sampler + models.better.ncsnpp_more.UNetMore_DDPM, imported unmodified
+    from baseline/_ref (or $EVC_REF, /root/reference), fp32, B=1, random init (torch.manual_seed(0)).  One call of the
+    reference sampler with subsample_steps=n_steps runs n_steps + 1 UNet evaluations (n_steps updates + the final
+    denoise evaluation) through its stock code path; the per-evaluation time is extrapolated to the 101 of DDPM-100."""
+    import common
+    root = find_reference()
+    sys.dont_write_bytecode = True
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import models as ref_models  # the reference package (ours is evcdiff.models)
+    from models.better.ncsnpp_more import UNetMore_DDPM as RefNet
+    torch.set_num_threads(threads)
+    global _REF_NET
+    cfg = common.full_config()
+    if _REF_NET is None:
+        torch.manual_seed(0)
+        _REF_NET = RefNet(cfg).eval()
+    torch.manual_seed(1234)
+    x = torch.randn(1, 15, 128, 128)
+    cond = torch.from_numpy(synthetic_videos(1)[:, :2].reshape(1, 6, 128, 128)).double() / 255.0 * 2 - 1
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        ref_models.ddpm_sampler(x, _REF_NET, cond=cond, final_only=True, denoise=True, subsample_steps=n_steps,
+                                clip_before=True, verbose=False, log=False)
+        dt = time.perf_counter() - t0
+    s_per_eval = dt / (n_steps + 1)
+    return 5.0 / (101 * s_per_eval), s_per_eval
+
+
+def port_cpu_fps(n_evals, threads):
+    """Fallback when no copy of the reference is reachable: the oracle port of the same path (oracle/ncsnpp.py +
+    the DDPM update of oracle/samplers.py), B=1, `n_evals` evaluations timed, extrapolated to 101."""
     import common
     from oracle import ncsnpp as O
     from oracle import samplers as S
@@ -114,12 +159,9 @@ def cpu_reference_fps(n_evals, threads):
     g = torch.Generator().manual_seed(1234)
     x = torch.randn(1, 15, 128, 128, generator=g)
     cond = torch.rand(1, 6, 128, 128, generator=g, dtype=torch.float64) * 2 - 1
-    sched = S.schedule(cfg)
+    betas, alphas, alphas_prev = S.schedule(cfg)
     model = lambda xx, yy: O.ncsnpp_forward(sd, cfg, xx, yy, cond)
-    betas, alphas, alphas_prev = sched
-    # one untimed evaluation (page-in, thread pool), then n_evals timed DDPM steps
     with torch.no_grad():
-        model(x, torch.zeros(1, dtype=torch.long))
         steps, a, ap, b = S._subsample(alphas, alphas_prev, betas, 100)
         t0 = time.perf_counter()
         for i in range(n_evals):
@@ -133,40 +175,72 @@ def cpu_reference_fps(n_evals, threads):
     return 5.0 / (101 * s_per_eval), s_per_eval
 
 
+def cpu_baseline(n_evals, one_thread=True):
+    """cpu_baseline object of the JSON line: all host cores (bounded sample) + the 1-thread figure -- city_sender.py
+    runs with torch.set_num_threads(1) because importing Inference.py executes it (Inference.py:15)."""
+    cores = os.cpu_count() or 1
+    ref = find_reference()
+    if ref is not None:
+        reference_cpu_fps(1, cores)  # untimed: page-in, thread pool
+        fps, spe = reference_cpu_fps(max(n_evals - 1, 1), cores)
+        kind, what = "reference", f"unmodified reference models.ddpm_sampler + UNetMore_DDPM from {os.path.relpath(ref, ROOT) if ref.startswith(ROOT) else ref}"
+    else:
+        port_cpu_fps(1, cores)
+        fps, spe = port_cpu_fps(n_evals, cores)
+        kind, what = "port", "oracle fp32 torch port of the reference (no copy of the reference reachable)"
+    out = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+           "sample": f"B=1, {n_evals} of the 101 UNet evaluations of one DDPM-100 cycle ({what}, fp32, {cores} host threads), "
+                     f"extrapolated x101; {spe:.3f} s/evaluation"}
+    if one_thread:
+        f1, s1 = (reference_cpu_fps(1, 1) if ref is not None else port_cpu_fps(1, 1))
+        out["value_1thread"] = f1
+        out["sample_1thread"] = (f"same code with torch.set_num_threads(1) (what city_sender.py runs with, Inference.py:15): "
+                                 f"2 evaluations, {s1:.2f} s/evaluation" if ref is not None else f"1 evaluation, {s1:.2f} s")
+        torch.set_num_threads(cores)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    ref = find_reference()
+    fn = (lambda n: reference_cpu_fps(max(n - 1, 1), cores)) if ref is not None else (lambda n: port_cpu_fps(n, cores))
     vals = []
     for _ in range(args.warmup):
-        cpu_reference_fps(1, cores)
+        fn(2)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        fps, spe = cpu_reference_fps(args.ref_evals, cores)
-        vals.append((fps, spe))
+        vals.append(fn(args.ref_evals))
     wall = time.perf_counter() - t0
     fps = sum(v[0] for v in vals) / len(vals)
     spe = sum(v[1] for v in vals) / len(vals)
-    sample = (f"B=1, {args.ref_evals} of the 101 UNet evaluations of one DDPM-100 cycle per step (oracle fp32 torch on "
-              f"{cores} host threads), extrapolated x101; {spe:.3f} s/evaluation")
+    kind = "reference" if ref is not None else "port"
+    what = ("the unmodified reference (models.ddpm_sampler + UNetMore_DDPM, stock code path, imported from "
+            f"{os.path.relpath(ref, ROOT) if ref.startswith(ROOT) else ref})") if ref is not None else "oracle fp32 torch port"
+    sample = (f"B=1 (the reference samples one video per call, city_sender.py:526), {args.ref_evals} of the 101 UNet "
+              f"evaluations of one DDPM-100 cycle per step, {what} on {cores} host threads, extrapolated x101; "
+              f"{spe:.3f} s/evaluation")
     line = {"impl": "reference", "metric": "predicted frames/s (128x128)", "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, 1),
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def workload_config(args, world):
-    return {"workload": f"BASELINE.json configs[1]: city_bonn-shaped synthetic set, {args.videos} videos per GPU, "
+    per = "in total, sharded by video over the GPUs" if args.scaling == "strong" else "per GPU"
+    return {"workload": f"BASELINE.json configs[1]: city_bonn-shaped synthetic set, {args.videos} videos {per}, "
                         f"{args.sampler.upper()}-{args.subsample} ({EVALS[args.sampler](args.subsample)} UNet evaluations per "
                         f"cycle), {MODEL_NAME[args.model]}, random init, 5 predicted 128x128 frames per "
                         f"video per step",
-            "model": args.model, "precision": args.precision,
-            "videos_per_gpu": args.videos, "sampler": args.sampler, "subsample": args.subsample,
-            "micro_batch": args.micro_batch, "parallelism": f"shard-by-video x{world}, one NCCL gather per step",
+            "model": args.model, "precision": args.precision, "scaling": args.scaling,
+            "videos": args.videos, "sampler": args.sampler, "subsample": args.subsample,
+            "micro_batch": args.micro_batch, "gather": args.gather,
+            "parallelism": f"shard-by-video x{world}, global-seed noise sliced per rank, one NCCL gather per step",
             "l2": "working set (>= 2 GB of activations per evaluation) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -176,17 +250,22 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--videos", type=int, default=46, help="videos per GPU (city_bonn.npy has 46)")
-    ap.add_argument("--micro-batch", type=int, default=46)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): --videos is the GLOBAL set, sharded by video over the ranks (BASELINE configs[1]: "
+                         "46 videos over 8 GPUs = 6/6/6/6/6/6/5/5); weak: --videos per rank")
+    ap.add_argument("--videos", type=int, default=46, help="videos (city_bonn.npy has 46)")
+    ap.add_argument("--micro-batch", type=int, default=64, help="largest batch sampled at once on one GPU")
     ap.add_argument("--sampler", default="ddpm", choices=["ddpm", "ddim", "fpndm"])
     ap.add_argument("--subsample", type=int, default=100)
     ap.add_argument("--model", default="ncsnpp", choices=["ncsnpp", "unet_deep", "unet_deeper"],
-                    help="ncsnpp = BASELINE configs[1-4]; unet_* = configs[4] (models/unet.py variant)")
+                    help="ncsnpp = BASELINE configs[0-3]; unet_* = configs[4] (models/unet.py variant)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16 (default, the metric's dtype) | fp32 = split-bf16 x3 arithmetic (1e-3 tolerance mode)")
+    ap.add_argument("--gather", default="fp32", choices=["fp32", "uint8"], help="format of the end-of-step frame gather")
     ap.add_argument("--ref-evals", type=int, default=4)
     ap.add_argument("--cpu-evals", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="skip the per-launch roofline pass")
     ap.add_argument("--profile-json", default=None, help="write the per-launch timing table of one evaluation here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -220,32 +299,42 @@ def main():
         net = UNet_DDPM(cfg).to(dev).eval()
     net.precision = args.precision
 
-    videos = synthetic_videos(args.videos, seed=rank)
-    data = torch.from_numpy(videos[:, :2].reshape(args.videos, 6, 128, 128)).double() / 255.0  # city_sender.py:487
+    # strong: every rank holds the same global set and samples its contiguous shard; weak: a rank's own set (seed = rank)
+    strong = args.scaling == "strong"
+    V = args.videos
+    videos = synthetic_videos(V, seed=0 if strong else rank)
+    data = torch.from_numpy(videos[:, :2].reshape(V, 6, 128, 128)).double() / 255.0  # city_sender.py:487
     if args.model != "ncsnpp":
         data = data.float()  # models/unet.py never casts its input (a float64 cond crashes the reference's first conv)
+    lo, hi = pipeline.shard_range(V, rank, world) if strong else (0, V)
+    n_local = hi - lo
     host_in = data.pin_memory()
-    host_out = torch.empty((args.videos, 5, 3, 128, 128), dtype=torch.float32).pin_memory()
+    host_out = torch.empty((V, 5, 3, 128, 128), dtype=torch.uint8 if args.gather == "uint8" else torch.float32).pin_memory()
     dev_in = host_in.to(dev)
-    torch.manual_seed(1234 + rank)
-    torch.cuda.manual_seed_all(1234 + rank)
     sampler = args.sampler.upper()
-    kw = dict(config=cfg, sampler=sampler, max_batch=args.micro_batch)
-    gather_buf = None
-    if world > 1 and rank == 0:
-        gather_buf = [torch.empty((args.videos, 5, 3, 128, 128), device=dev) for _ in range(world)]
+    kw = dict(config=cfg, sampler=sampler, max_batch=args.micro_batch, gather=args.gather)
+    weak_buf = None
+    if not strong and world > 1 and rank == 0:
+        weak_buf = [torch.empty((V, 5, 3, 128, 128), device=dev) for _ in range(world)]
 
-    def step_device():
-        fr = pipeline.generate_frame(net, dev_in, to_host=False, **kw)
+    def step(inp):
+        """One sampling cycle of the whole job: 5 predicted frames for every video.  The Gaussian draws are those a
+        single GPU would make for the global batch from seed 1234 (x_T, then one draw per non-final DDPM step), sliced
+        per rank; predicted frames are gathered on rank 0."""
+        if strong:
+            return pipeline.generate_frame_sharded(net, inp, rank, world, seed=1234, **kw)
+        fr = pipeline.generate_frame_sharded(net, inp, 0, 1, seed=1234 + rank, **kw)
         if world > 1:
-            dist.gather(fr.contiguous(), gather_buf, dst=0)
+            dist.gather(fr.contiguous(), weak_buf, dst=0)
         return fr
 
+    def step_device():
+        return step(dev_in)
+
     def step_e2e():
-        fr = pipeline.generate_frame(net, host_in, to_host=False, **kw)  # H2D of the conditioning frames inside
-        if world > 1:
-            dist.gather(fr.contiguous(), gather_buf, dst=0)
-        host_out.copy_(fr, non_blocking=True)  # D2H of the predicted frames
+        fr = step(host_in)  # H2D of this rank's conditioning frames (pinned host memory) inside
+        if rank == 0:
+            host_out[: fr.shape[0]].copy_(fr, non_blocking=True)  # D2H of the gathered predicted frames
         return fr
 
     def timed(fn, n):
@@ -273,79 +362,85 @@ def main():
         clocks.start()
     n0 = ops.launch_count()
     ms = timed(step_device, args.steps)
-    eng = net.engine(min(args.micro_batch, args.videos), dev)
+    mb = min(args.micro_batch, max(n_local, 1))
+    eng = net.engine(mb, dev)
     loop = eng._loop
     per_run = max(loop.launches_per_run.values()) if loop.launches_per_run else 0
-    micro = -(-args.videos // args.micro_batch)
+    micro = -(-n_local // args.micro_batch)
     gpu_launches = (ops.launch_count() - n0) + args.steps * micro * per_run  # graph replays re-run the captured launches
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop() if rank == 0 else None
 
-    frames_per_step = args.videos * 5 * world
+    frames_per_step = V * 5 * (1 if strong else world)
     value = frames_per_step * args.steps / (ms / 1e3)
     e2e = frames_per_step * args.steps / (ms_e2e / 1e3)
     evals = EVALS[args.sampler](args.subsample)
     tflop_per_frame = GFLOP[args.model] * evals / 5.0 / 1e3
 
-    # ---- roofline of the dominant kernel (evc_gemm_kernel): CUDA events around every launch of one evaluation
-    prof = eng.profile(0, reps=3)
-    gemm_ms = sum(t for k, m, t in prof if k == "gemm")
-    gemm_fl = sum(m["flops"] for k, m, t in prof if k == "gemm")
-    tot_ms = sum(t for k, m, t in prof)
-    by_kind = {}
-    for k, m, t in prof:
-        by_kind[k] = by_kind.get(k, 0.0) + t
-    achieved_all = gemm_fl / (gemm_ms / 1e3) / 1e12
-    # dominant kernel launch: the most expensive GEMM shape of the evaluation (192->192 3x3 at 128x128 for configs/mine.yml)
-    shapes = {}
-    for k, m, t in prof:
-        if k == "gemm":
-            key = (m["M"], m["N"], m["K"])
-            e = shapes.setdefault(key, [0, 0.0, 0.0])
-            e[0] += 1
-            e[1] += t
-            e[2] += m["flops"]
-    dom_key, dom = max(shapes.items(), key=lambda kv: kv[1][1])
-    achieved = dom[2] / (dom[1] / 1e3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tpath):  # DRAM bytes per launch from the committed ncu --set full capture of this shape
-        with open(tpath) as f:
-            tj = json.load(f).get("shapes", {}).get("x".join(str(v) for v in dom_key))
-        if tj is not None:
-            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-    roofline = {"bound": "tensor", "kernel": "evc_gemm_kernel",
-                "launch": f"M={dom_key[0]} N={dom_key[1]} K={dom_key[2]} ({dom[0]} launches per evaluation, "
-                          f"{dom[2] / dom[0] / 1e9:.1f} GFLOP each)",
-                "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_sustained"], "traffic": traffic,
-                "peak_source": pk["source"] + ", bf16 dense sustained",
-                "all_gemm_launches": {"achieved": achieved_all, "frac": achieved_all / pk["bf16_sustained"],
-                                      "share_of_eval": gemm_ms / tot_ms},
-                "ms_per_eval_by_kernel": {k: round(v, 3) for k, v in by_kind.items()},
-                "step_tensor_frac": value / world * tflop_per_frame / pk["bf16_sustained"]}
-    if args.profile_json and rank == 0:
-        with open(args.profile_json, "w") as f:
-            json.dump([{"kind": k, "ms": t, **({} if m is None else {kk: vv for kk, vv in m.items()})} for k, m, t in prof], f)
+    roofline = None
+    if not args.no_profile:
+        # ---- roofline of the dominant kernel (evc_gemm_kernel): CUDA events around every launch of one evaluation
+        prof = eng.profile(0, reps=3)
+        gemm_ms = sum(t for k, m, t in prof if k == "gemm")
+        gemm_fl = sum(m["flops"] for k, m, t in prof if k == "gemm")
+        tot_ms = sum(t for k, m, t in prof)
+        by_kind = {}
+        for k, m, t in prof:
+            by_kind[k] = by_kind.get(k, 0.0) + t
+        achieved_all = gemm_fl / (gemm_ms / 1e3) / 1e12
+        # dominant kernel launch: the most expensive GEMM shape of the evaluation (384->192 3x3 at 128x128 for configs/mine.yml)
+        shapes = {}
+        for k, m, t in prof:
+            if k == "gemm":
+                key = (m["M"], m["N"], m["K"])
+                e = shapes.setdefault(key, [0, 0.0, 0.0])
+                e[0] += 1
+                e[1] += t
+                e[2] += m["flops"]
+        dom_key, dom = max(shapes.items(), key=lambda kv: kv[1][1])
+        achieved = dom[2] / (dom[1] / 1e3) / 1e12
+        traffic, traffic_src = None, None
+        import glob
+        for tpath in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")), reverse=True):
+            # DRAM bytes per launch from the newest committed `ncu --set full` capture of this launch shape (static: ncu
+            # cannot run inside the timed benchmark)
+            with open(tpath) as f:
+                tj = json.load(f).get("shapes", {}).get("x".join(str(v) for v in dom_key))
+            if tj is not None:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                traffic_src = f"static ncu --set full capture, {os.path.relpath(tpath, ROOT)}"
+                break
+        roofline = {"bound": "tensor", "kernel": "evc_gemm_kernel",
+                    "launch": f"M={dom_key[0]} N={dom_key[1]} K={dom_key[2]} ({dom[0]} launches per evaluation, "
+                              f"{dom[2] / dom[0] / 1e9:.1f} GFLOP each)",
+                    "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["bf16_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": pk["source"] + ", bf16 dense sustained",
+                    "all_gemm_launches": {"achieved": achieved_all, "frac": achieved_all / pk["bf16_sustained"],
+                                          "share_of_eval": gemm_ms / tot_ms},
+                    "ms_per_eval_by_kernel": {k: round(v, 3) for k, v in by_kind.items()},
+                    "batch_profiled": mb,
+                    "step_tensor_frac": value / world * tflop_per_frame / pk["bf16_sustained"]}
+        if args.profile_json and rank == 0:
+            with open(args.profile_json, "w") as f:
+                json.dump([{"kind": k, "ms": t, **({} if m is None else {kk: vv for kk, vv in m.items()})} for k, m, t in prof], f)
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            fps, spe = cpu_reference_fps(args.cpu_evals, cores)
-            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                   "sample": f"B=1, {args.cpu_evals} of the 101 UNet evaluations of one DDPM-100 cycle (oracle fp32 torch port of "
-                             f"the reference, {cores} host threads), extrapolated x101; {spe:.3f} s/evaluation"}
+        if not args.no_cpu_baseline and world == 1:
+            cpu = cpu_baseline(args.cpu_evals)
         line = {"metric": "predicted frames/s (128x128)", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None,
+                "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (split hi/lo operands, fp32 accumulate)",
                 "data": "synthetic", "config": workload_config(args, world), "clocks": clk,
                 "e2e": {"value": e2e, "unit": "frames/s",
                         "h2d_bytes_per_step": host_in.numel() * host_in.element_size(),
                         "d2h_bytes_per_step": host_out.numel() * host_out.element_size()},
                 "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu,
+                "videos_per_gpu": [pipeline.shard_range(V, r, world)[1] - pipeline.shard_range(V, r, world)[0]
+                                   for r in range(world)] if strong else [V] * world,
                 "tflops_per_gpu": value / world * tflop_per_frame}
         print(json.dumps(line), flush=True)
     if world > 1:

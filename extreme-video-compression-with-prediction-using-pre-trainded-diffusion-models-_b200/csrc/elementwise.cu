@@ -759,6 +759,24 @@ __global__ void inverse_transform_kernel(const float* __restrict__ x, float* __r
   }
 }
 
+// frames in [0,1] fp32 -> uint8 round(255 x) (round half to even, like numpy / torch round), 4 values per thread
+__global__ void frames_to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, long long n) {
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    uchar4 o;
+    o.x = (unsigned char)fminf(fmaxf(rintf(v.x * 255.f), 0.f), 255.f);
+    o.y = (unsigned char)fminf(fmaxf(rintf(v.y * 255.f), 0.f), 255.f);
+    o.z = (unsigned char)fminf(fmaxf(rintf(v.z * 255.f), 0.f), 255.f);
+    o.w = (unsigned char)fminf(fmaxf(rintf(v.w * 255.f), 0.f), 255.f);
+    reinterpret_cast<uchar4*>(y)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = n4 * 4 + threadIdx.x;
+    y[i] = (unsigned char)fminf(fmaxf(rintf(x[i] * 255.f), 0.f), 255.f);
+  }
+}
+
 }  // namespace evc
 
 using namespace evc;
@@ -1030,4 +1048,11 @@ extern "C" int evc_inverse_transform(const float* x, float* frames, int64_t n, e
   if (!x || !frames || n < 1) return evc_set_error(EVC_ERR_INVALID, "evc_inverse_transform: bad arguments");
   inverse_transform_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, frames, n);
   return evc_check_launch("inverse_transform_kernel");
+}
+
+extern "C" int evc_frames_to_uint8(const float* frames, uint8_t* out, int64_t n, evc_stream_t stream) {
+  if (!frames || !out || n < 1 || (reinterpret_cast<uintptr_t>(frames) & 15) || (reinterpret_cast<uintptr_t>(out) & 3))
+    return evc_set_error(EVC_ERR_INVALID, "evc_frames_to_uint8: bad arguments (frames 16-byte, out 4-byte aligned)");
+  frames_to_uint8_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(frames, out, n);
+  return evc_check_launch("frames_to_uint8_kernel");
 }

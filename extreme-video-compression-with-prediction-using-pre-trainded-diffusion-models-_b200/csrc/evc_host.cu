@@ -70,13 +70,13 @@ int evc_pdl_enabled() {
 extern "C" void evc_set_pdl(int enabled) { g_pdl.store(enabled ? 1 : 0); }
 
 int evc_num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    int v = 0;
+  static std::atomic<int> sms[64];  // per device: plans are created for the current device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int v = sms[dev].load();
+  if (v == 0) {
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
-    sms = v;
+    sms[dev].store(v);
   }
-  return sms;
+  return v;
 }

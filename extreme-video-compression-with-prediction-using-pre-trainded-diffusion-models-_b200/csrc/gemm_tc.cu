@@ -32,6 +32,9 @@ constexpr int kAccStride = 256;  // TMEM columns between the two accumulator sta
 
 constexpr int kMaxVSeg = 9;
 
+// Fused GroupNorm apply: number of tile waits that gave up (see gn_pass2).  Read by evc_gemm_fault_count().
+__device__ unsigned int g_gn_wait_faults = 0;
+
 #ifdef EVC_GEMM_PROF
 // Wait-time probe (tools/gpu_gemm_waits.py; never compiled into the shipped library):
 // [0] MMA warp total, [1] MMA waits on full (operands), [2] MMA waits on tempty (accumulator),
@@ -393,11 +396,16 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         do {
           asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.gn_ticket + pb) : "memory");
           if (seen < p.tiles_per_sample) {
-            __nanosleep(32);
-            // all CTAs of the grid are co-resident (grid <= SM count, one CTA per SM), so the other tiles are always
-            // making progress; a wait of seconds means a caller error (tickets not zeroed, foreign work holding SMs):
-            // fail the launch instead of hanging the device
-            if (clock64() - t0 > (1ll << 33)) __trap();
+            __nanosleep(64);
+            // The plan guarantees (host side, evc_gemm_plan_create) that no CTA waits for a tile it owns itself and
+            // that the whole grid fits on the device at once, so the other tiles are being computed and this wait ends;
+            // foreign work holding SMs only delays it.  After ~10 s at any clock the caller broke the contract (tickets
+            // not zeroed): count a fault and carry on with the statistics that are there -- wrong numbers for this
+            // sample, reported through evc_gemm_fault_count(), instead of a hung or trapped context.
+            if (clock64() - t0 > (1ll << 34)) {
+              atomicAdd(&g_gn_wait_faults, 1u);
+              break;
+            }
           }
         } while (seen < p.tiles_per_sample);
       }
@@ -873,6 +881,18 @@ struct evc_gemm_plan {
   double flops;
 };
 
+static cudaError_t ensure_gemm_attrs() {
+  static bool attr_set = false;
+  if (attr_set) return cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  void (*kernels[4])(GemmParams) = {evc_gemm_kernel<1, false>, evc_gemm_kernel<2, false>, evc_gemm_kernel<1, true>,
+                                    evc_gemm_kernel<2, true>};
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+    e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) attr_set = true;
+  return e;
+}
+
 static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, int conv_stride = 1, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = evc_get_encode_tiled();
@@ -1132,6 +1152,32 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
                            "fused GroupNorm apply needs stats + ticket + bias, no residual, alpha 1, bf16 rows through the "
                            "TMA-store epilogue (H*W % 128 == 0, W <= 128, bn % 32 == 0) and N % groups == 0");
     }
+    // (a) a CTA normalises tile k only after accumulating its tile k+1, and waits there for every tile of the sample:
+    //     it must not own a third tile of the same sample (units are handed out round robin, `num_units` apart);
+    // (b) all CTAs must be resident together (they wait for each other): one CTA per SM / one pair per SM pair.
+    {
+      const int cap = (d->max_ctas > 0 ? d->max_ctas : evc_num_sms()) / cg;
+      const long long units_total = (long long)((p.m_tiles + cg - 1) / cg) * p.tiles_n;
+      const long long num_units = units_total < cap ? units_total : cap;
+      const long long sample_units = ((long long)p.tiles_x * p.tiles_y + cg - 1) / cg * p.tiles_n + (cg > 1 ? p.tiles_n : 0);
+      int resident = 0;
+      const int smem_need = 227 * 1024;
+      cudaError_t oe = ensure_gemm_attrs();
+      if (oe == cudaSuccess)
+        oe = cg == 2
+          ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, evc_gemm_kernel<2, false>, kThreads, smem_need)
+          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, evc_gemm_kernel<1, false>, kThreads, smem_need);
+      if (oe != cudaSuccess) {
+        (void)cudaGetLastError();
+        resident = 1;  // no device here (plan built for inspection only): the launch itself would fail first
+      }
+      if (sample_units > 2 * num_units || resident < 1 || num_units * cg > (long long)resident * evc_num_sms()) {
+        delete pl;
+        return evc_set_error(EVC_ERR_UNSUPPORTED,
+                             "fused GroupNorm apply: a sample has more tiles than two rounds of the persistent grid (or the "
+                             "grid cannot be co-resident); use the unfused gn_apply path for this shape");
+      }
+    }
     p.gn_fuse = 1;
     p.gn_ss = d->gn_ss;
     p.gn_ticket = d->gn_ticket;
@@ -1163,27 +1209,29 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
 }
 
 extern "C" int evc_gemm_plan_launch(const evc_gemm_plan* pl, const float* bias_override, evc_stream_t stream) {
-  return evc_gemm_plan_launch_gn(pl, bias_override, nullptr, stream);
+  return evc_gemm_plan_launch_ex(pl, bias_override, nullptr, nullptr, stream);
 }
 
 extern "C" int evc_gemm_plan_launch_gn(const evc_gemm_plan* pl, const float* bias_override, const float* gn_ss_override,
                                        evc_stream_t stream) {
+  return evc_gemm_plan_launch_ex(pl, bias_override, gn_ss_override, nullptr, stream);
+}
+
+extern "C" int evc_gemm_plan_launch_ex(const evc_gemm_plan* pl, const float* bias_override, const float* gn_ss_override,
+                                       void* out_override, evc_stream_t stream) {
   if (pl == nullptr) return evc_set_error(EVC_ERR_INVALID, "null plan");
   if (gn_ss_override != nullptr && !pl->p.gn_fuse)
     return evc_set_error(EVC_ERR_INVALID, "gn_ss_override on a plan without fused GroupNorm apply");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaSuccess;
-    void (*kernels[4])(GemmParams) = {evc_gemm_kernel<1, false>, evc_gemm_kernel<2, false>, evc_gemm_kernel<1, true>,
-                                      evc_gemm_kernel<2, true>};
-    for (int i = 0; i < 4 && e == cudaSuccess; ++i)
-      e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
-    attr_set = true;
+  if (out_override != nullptr && (pl->p.tma_out != 0 || pl->split))
+    return evc_set_error(EVC_ERR_INVALID, "out_override needs a per-thread-store output (fp32 / transposed modes)");
+  {
+    cudaError_t ae = ensure_gemm_attrs();
+    if (ae != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(ae));
   }
   GemmParams p = pl->p;
   if (bias_override != nullptr) p.bias = bias_override;
   if (gn_ss_override != nullptr) p.gn_ss = gn_ss_override;
+  if (out_override != nullptr) p.out = out_override;
   cudaError_t e;
   const bool split = pl->split;
   void (*kernel)(GemmParams) = pl->cg == 2 ? (split ? evc_gemm_kernel<2, true> : evc_gemm_kernel<2, false>)
@@ -1191,6 +1239,18 @@ extern "C" int evc_gemm_plan_launch_gn(const evc_gemm_plan* pl, const float* bia
   e = evc_launch(kernel, dim3(pl->grid), dim3(kThreads), pl->smem_bytes, (cudaStream_t)stream, pl->cg, p);
   if (e != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(e));
   return evc_check_launch(pl->cg == 2 ? "evc_gemm_kernel<2>" : "evc_gemm_kernel<1>");
+}
+
+// Synchronising debug query: how many fused-GroupNorm tile waits gave up since the last call (0 unless a caller broke
+// the ticket contract).  Not for use inside stream capture.
+extern "C" int64_t evc_gemm_fault_count(void) {
+  unsigned int v = 0, z = 0;
+  if (cudaMemcpyFromSymbol(&v, evc::g_gn_wait_faults, sizeof(v)) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return -1;
+  }
+  if (v != 0) (void)cudaMemcpyToSymbol(evc::g_gn_wait_faults, &z, sizeof(z));
+  return (int64_t)v;
 }
 
 extern "C" int evc_gemm_plan_cta_group(const evc_gemm_plan* pl) { return pl ? pl->cg : 0; }

@@ -7,39 +7,18 @@
 
 namespace evc {
 
-// One thread per pixel: per channel plane the warp reads/writes 128 contiguous bytes of fp32; the bf16
-// NHWC row (C <= 32 values) is written as one short run per thread.
-__global__ void sampler_update_kernel(const float* __restrict__ x, const float* __restrict__ eps,
-                                      const float* __restrict__ noise, float* __restrict__ x_out,
-                                      __nv_bfloat16* __restrict__ xin, int B, int C, int HW, int Cpad,
-                                      evc_step_coef k) {
-  pdl_wait();
-  pdl_trigger();
-  const long long total = (long long)B * HW;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / HW);
-    const int p = (int)(i % HW);
-    const long long base = (long long)b * C * HW + p;
-    __nv_bfloat16* row = xin ? xin + i * Cpad : nullptr;
-    for (int c = 0; c < C; ++c) {
-      const long long idx = base + (long long)c * HW;
-      const float xv = x[idx];
-      const float ev = eps[idx];
-      float r;
-      if (k.mode == 0) {
-        // x0 = (1/sqrt(a)) * (x - sqrt(1-a)*eps)
-        float x0 = __fmul_rn(k.k0, __fsub_rn(xv, __fmul_rn(k.k1, ev)));
-        if (k.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-        r = __fadd_rn(__fmul_rn(k.c_x0, x0), __fmul_rn(k.c_x, xv));
-        if (k.c_eps != 0.f) r = __fadd_rn(r, __fmul_rn(k.c_eps, ev));
-        if (k.c_noise != 0.f) r = __fadd_rn(r, __fmul_rn(k.c_noise, noise[idx]));
-      } else {
-        r = __fsub_rn(xv, __fmul_rn(k.k1, ev));
-      }
-      x_out[idx] = r;
-      if (row) row[c] = __float2bfloat16_rn(r);
-    }
+// The update arithmetic, expression for expression as the reference evaluates it in fp32 (no fused multiply-adds).
+__device__ __forceinline__ float step_value(const evc_step_coef& k, float xv, float ev, float nz) {
+  if (k.mode == 0) {
+    // x0 = (1/sqrt(a)) * (x - sqrt(1-a)*eps)
+    float x0 = __fmul_rn(k.k0, __fsub_rn(xv, __fmul_rn(k.k1, ev)));
+    if (k.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    float r = __fadd_rn(__fmul_rn(k.c_x0, x0), __fmul_rn(k.c_x, xv));
+    if (k.c_eps != 0.f) r = __fadd_rn(r, __fmul_rn(k.c_eps, ev));
+    if (k.c_noise != 0.f) r = __fadd_rn(r, __fmul_rn(k.c_noise, nz));
+    return r;
   }
+  return __fsub_rn(xv, __fmul_rn(k.k1, ev));
 }
 
 struct PndmArgs {
@@ -47,9 +26,100 @@ struct PndmArgs {
   evc_pndm_coef k;
 };
 
-__global__ void pndm_update_kernel(const float* __restrict__ x, PndmArgs a, float* __restrict__ x_out,
-                                   float* __restrict__ et_out, __nv_bfloat16* __restrict__ xin, int B, int C, int HW,
-                                   int Cpad) {
+__device__ __forceinline__ float pndm_value(const evc_pndm_coef& k, float xv, const float (&e)[4], float& et) {
+  et = __fmul_rn(k.w[0], e[0]);
+#pragma unroll
+  for (int j = 1; j < 4; ++j)
+    if (j < k.n_e) et = __fadd_rn(et, __fmul_rn(k.w[j], e[j]));
+  et = __fmul_rn(et, k.w_scale);
+  // x' = x + d * (p*x - q*et)
+  float r = __fadd_rn(xv, __fmul_rn(k.d, __fsub_rn(__fmul_rn(k.p, xv), __fmul_rn(k.q, et))));
+  if (k.clip) r = fminf(fmaxf(r, -1.f), 1.f);
+  return r;
+}
+
+// Vectorised form (HW % 4 == 0, 16-byte aligned planes): a thread owns 4 consecutive pixels of one sample.  Per
+// channel plane it moves float4s (a warp touches 512 contiguous bytes per load / store instruction), and it writes the
+// bf16 NHWC UNet-input rows of its pixels as whole 16-byte chunks: channels [0, CP) with CP = C rounded up to 8, pad
+// channels zero (the conditioning frames start at channel CP, see evc_sampler_update in evcdiff.h).
+// PNDM = false: DDPM / DDIM / denoise update; PNDM = true: transfer with the fused multistep combination.
+template <int CP, bool PNDM>
+__global__ void __launch_bounds__(256) state_update_vec_kernel(const float* x, const float* __restrict__ eps,
+                                                               const float* __restrict__ noise, PndmArgs pa,
+                                                               float* x_out, float* __restrict__ et_out,
+                                                               __nv_bfloat16* __restrict__ xin, int B, int C, int HW,
+                                                               int Cpad, evc_step_coef k) {
+  pdl_wait();
+  pdl_trigger();
+  const long long groups = (long long)B * HW / 4;
+  const bool use_noise = !PNDM && k.mode == 0 && k.c_noise != 0.f;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += (long long)gridDim.x * blockDim.x) {
+    const long long pix = gi * 4;  // first of 4 consecutive pixels (same sample: HW % 4 == 0)
+    const int b = (int)(pix / HW);
+    const int p = (int)(pix % HW);
+    const long long base = (long long)b * C * HW + p;
+    uint32_t packed[4][CP / 2];  // [pixel][channel pair]
+#pragma unroll
+    for (int c = 0; c < CP; c += 2) {
+      float r[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = c + h;
+        if (cc < C) {
+          const long long idx = base + (long long)cc * HW;
+          const float4 xv = *reinterpret_cast<const float4*>(x + idx);  // x_out may alias x: plain load, no restrict
+          float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+          if (PNDM) {
+            float ea[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < pa.k.n_e) {
+                const float4 ev = __ldg(reinterpret_cast<const float4*>(pa.e[j] + idx));
+                ea[0][j] = ev.x; ea[1][j] = ev.y; ea[2][j] = ev.z; ea[3][j] = ev.w;
+              } else {
+                ea[0][j] = ea[1][j] = ea[2][j] = ea[3][j] = 0.f;
+              }
+            }
+            float et[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r[h][q] = pndm_value(pa.k, xa[q], ea[q], et[q]);
+            if (et_out) *reinterpret_cast<float4*>(et_out + idx) = make_float4(et[0], et[1], et[2], et[3]);
+          } else {
+            const float4 ev = __ldg(reinterpret_cast<const float4*>(eps + idx));
+            float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (use_noise) nv = __ldg(reinterpret_cast<const float4*>(noise + idx));
+            r[h][0] = step_value(k, xa[0], ev.x, nv.x);
+            r[h][1] = step_value(k, xa[1], ev.y, nv.y);
+            r[h][2] = step_value(k, xa[2], ev.z, nv.z);
+            r[h][3] = step_value(k, xa[3], ev.w, nv.w);
+          }
+          *reinterpret_cast<float4*>(x_out + idx) = make_float4(r[h][0], r[h][1], r[h][2], r[h][3]);
+        } else {
+          r[h][0] = r[h][1] = r[h][2] = r[h][3] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) packed[q][c / 2] = pack_bf16x2(r[0][q], r[1][q]);
+    }
+    if (xin != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4* row = reinterpret_cast<uint4*>(xin + (pix + q) * Cpad);
+#pragma unroll
+        for (int v = 0; v < CP / 8; ++v)
+          row[v] = make_uint4(packed[q][4 * v], packed[q][4 * v + 1], packed[q][4 * v + 2], packed[q][4 * v + 3]);
+      }
+    }
+  }
+}
+
+// Scalar form for shapes the vectorised kernel does not take (HW % 4 != 0, misaligned views, C > 32): one thread per
+// pixel; same row convention (channels [C, CP) are written as zero).
+template <bool PNDM>
+__global__ void state_update_scalar_kernel(const float* x, const float* __restrict__ eps,
+                                           const float* __restrict__ noise, PndmArgs pa, float* x_out,
+                                           float* __restrict__ et_out, __nv_bfloat16* __restrict__ xin, int B, int C, int HW,
+                                           int Cpad, int CP, evc_step_coef k) {
   pdl_wait();
   pdl_trigger();
   const long long total = (long long)B * HW;
@@ -60,17 +130,22 @@ __global__ void pndm_update_kernel(const float* __restrict__ x, PndmArgs a, floa
     __nv_bfloat16* row = xin ? xin + i * Cpad : nullptr;
     for (int c = 0; c < C; ++c) {
       const long long idx = base + (long long)c * HW;
-      float et = __fmul_rn(a.k.w[0], a.e[0][idx]);
-      for (int j = 1; j < a.k.n_e; ++j) et = __fadd_rn(et, __fmul_rn(a.k.w[j], a.e[j][idx]));
-      et = __fmul_rn(et, a.k.w_scale);
-      const float xv = x[idx];
-      // x' = x + d * (p*x - q*et)
-      float r = __fadd_rn(xv, __fmul_rn(a.k.d, __fsub_rn(__fmul_rn(a.k.p, xv), __fmul_rn(a.k.q, et))));
-      if (a.k.clip) r = fminf(fmaxf(r, -1.f), 1.f);
+      float r;
+      if (PNDM) {
+        float e[4] = {0.f, 0.f, 0.f, 0.f}, et;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < pa.k.n_e) e[j] = pa.e[j][idx];
+        r = pndm_value(pa.k, x[idx], e, et);
+        if (et_out) et_out[idx] = et;
+      } else {
+        r = step_value(k, x[idx], eps[idx], (k.mode == 0 && k.c_noise != 0.f) ? noise[idx] : 0.f);
+      }
       x_out[idx] = r;
-      if (et_out) et_out[idx] = et;
       if (row) row[c] = __float2bfloat16_rn(r);
     }
+    if (row)
+      for (int c = C; c < CP && c < Cpad; ++c) row[c] = __float2bfloat16_rn(0.f);
   }
 }
 
@@ -172,6 +247,41 @@ static inline int grid_px(long long n) {
   return (int)g;
 }
 
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <bool PNDM>
+static int launch_state_update(const float* x, const float* eps, const float* noise, const PndmArgs& pa, float* x_out,
+                               float* et_out, void* xin, int B, int C, int HW, int Cpad, const evc_step_coef& k,
+                               cudaStream_t stream, const char* what) {
+  const int CP = (C + 7) / 8 * 8;
+  if (xin != nullptr && (CP > Cpad || (Cpad % 8) != 0))
+    return evc_set_error(EVC_ERR_INVALID, "state update: the UNet-input row must hold roundup8(C) channels (Cpad % 8 == 0)");
+  __nv_bfloat16* xi = reinterpret_cast<__nv_bfloat16*>(xin);
+  bool vec = (HW % 4) == 0 && CP <= 32 && aligned16(x) && aligned16(x_out) && aligned16(xin) &&
+             (et_out == nullptr || aligned16(et_out));
+  if (PNDM) {
+    for (int j = 0; j < pa.k.n_e; ++j) vec = vec && aligned16(pa.e[j]);
+  } else {
+    vec = vec && aligned16(eps) && (noise == nullptr || aligned16(noise));
+  }
+  cudaError_t le;
+  if (vec) {
+    const dim3 grid(grid_px((long long)B * HW / 4));
+    auto go = [&](auto kern) {
+      return evc_launch(kern, grid, dim3(256), 0, stream, 1, x, eps, noise, pa, x_out, et_out, xi, B, C, HW, Cpad, k);
+    };
+    if (CP <= 8) le = go(state_update_vec_kernel<8, PNDM>);
+    else if (CP <= 16) le = go(state_update_vec_kernel<16, PNDM>);
+    else if (CP <= 24) le = go(state_update_vec_kernel<24, PNDM>);
+    else le = go(state_update_vec_kernel<32, PNDM>);
+  } else {
+    le = evc_launch(state_update_scalar_kernel<PNDM>, dim3(grid_px((long long)B * HW)), dim3(256), 0, stream, 1, x, eps,
+                    noise, pa, x_out, et_out, xi, B, C, HW, Cpad, CP, k);
+  }
+  if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
+  return evc_check_launch(what);
+}
+
 extern "C" int evc_sampler_update(const float* x, const float* eps, const float* noise, float* x_out, void* xin,
                                   int32_t B, int32_t C, int32_t HW, int32_t Cpad, const evc_step_coef* coef_host,
                                   evc_stream_t stream) {
@@ -179,11 +289,10 @@ extern "C" int evc_sampler_update(const float* x, const float* eps, const float*
     return evc_set_error(EVC_ERR_INVALID, "evc_sampler_update: bad arguments");
   if (coef_host->mode == 0 && coef_host->c_noise != 0.f && noise == nullptr)
     return evc_set_error(EVC_ERR_INVALID, "evc_sampler_update: noise required");
-  cudaError_t le = evc_launch(sampler_update_kernel, dim3(grid_px((long long)B * HW)), dim3(256), 0, (cudaStream_t)stream, 1,
-                              x, eps, noise, x_out, reinterpret_cast<__nv_bfloat16*>(xin), (int)B, (int)C, (int)HW, (int)Cpad,
-                              *coef_host);
-  if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
-  return evc_check_launch("sampler_update_kernel");
+  PndmArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  return launch_state_update<false>(x, eps, noise, pa, x_out, nullptr, xin, B, C, HW, Cpad, *coef_host,
+                                    (cudaStream_t)stream, "sampler_update_kernel");
 }
 
 extern "C" int evc_pndm_update(const float* x, const float* const* e_host, float* x_out, float* et_out, void* xin,
@@ -197,10 +306,10 @@ extern "C" int evc_pndm_update(const float* x, const float* const* e_host, float
   for (int j = 0; j < coef_host->n_e; ++j)
     if (a.e[j] == nullptr) return evc_set_error(EVC_ERR_INVALID, "evc_pndm_update: null eps pointer");
   a.k = *coef_host;
-  cudaError_t le = evc_launch(pndm_update_kernel, dim3(grid_px((long long)B * HW)), dim3(256), 0, (cudaStream_t)stream, 1,
-                              x, a, x_out, et_out, reinterpret_cast<__nv_bfloat16*>(xin), (int)B, (int)C, (int)HW, (int)Cpad);
-  if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
-  return evc_check_launch("pndm_update_kernel");
+  evc_step_coef k;
+  memset(&k, 0, sizeof(k));
+  return launch_state_update<true>(x, nullptr, nullptr, a, x_out, et_out, xin, B, C, HW, Cpad, k, (cudaStream_t)stream,
+                                   "pndm_update_kernel");
 }
 
 extern "C" int evc_timestep_embedding(const float* labels, const float* freqs, int32_t L, int32_t dim, float* out,

@@ -63,6 +63,8 @@ SIGNATURES = {
     "evc_gemm_plan_create": (C.c_int, [C.POINTER(GemmDesc), C.POINTER(C.c_void_p)]),
     "evc_gemm_plan_launch": (C.c_int, [_vp, _vp, _vp]),
     "evc_gemm_plan_launch_gn": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "evc_gemm_plan_launch_ex": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "evc_gemm_fault_count": (C.c_int64, []),
     "evc_gemm_plan_destroy": (None, [_vp]),
     "evc_gemm_plan_flops": (C.c_double, [_vp]),
     "evc_gemm_plan_cta_group": (C.c_int, [_vp]),
@@ -91,6 +93,7 @@ SIGNATURES = {
     "evc_pndm_update": (C.c_int, [_vp, C.POINTER(C.c_void_p), _vp, _vp, _vp, _i32, _i32, _i32, _i32,
                                   C.POINTER(PndmCoef), _vp]),
     "evc_inverse_transform": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "evc_frames_to_uint8": (C.c_int, [_vp, _vp, _i64, _vp]),
     "evc_frame_psnr": (C.c_int, [_vp, _vp, _i32, _i64, C.c_double, _vp, _vp]),
     "evc_accept_prefix": (C.c_int, [_vp, _i32, _i32, C.c_double, _i32, _vp, _vp]),
 }

@@ -82,6 +82,22 @@ def pack_conv3(w, cin_pad=None):
     return w.reshape(co, -1).contiguous()
 
 
+def pack_conv_in(w, c_x, cin_pad):
+    """First conv of the UNet: (Cout, c_x + c_cond, 3, 3) -> packed K with the input-row layout of the sampler-update
+    kernels: [x_t (c_x) | zero pad to a multiple of 8 | cond (c_cond) | zero pad to cin_pad] (evc_sampler_update writes
+    x_t as whole 16-byte chunks, so the conditioning frames of the reference's torch.cat start at roundup8(c_x))."""
+    co, ci = w.shape[:2]
+    off = cond_offset(c_x)
+    w2 = torch.zeros((co, cin_pad, 3, 3), dtype=torch.float32, device=w.device)
+    w2[:, :c_x] = w[:, :c_x].float()
+    w2[:, off:off + ci - c_x] = w[:, c_x:].float()
+    return pack_conv3(w2)
+
+
+def cond_offset(c_x):
+    return (c_x + 7) // 8 * 8
+
+
 def split_bf16(w):
     """fp32 -> (hi, lo) bf16 planes with hi + lo = w to 2^-17."""
     hi = w.to(torch.bfloat16)
@@ -155,8 +171,12 @@ class EngineBase:
         if tw * th != 128 or W % tw or H % th:
             return False
         kblocks = sum(taps * (-(-c // 64)) for c, taps in cin_segs)
-        bn = ops.pick_bn(cout, ops.m_tiles(B, H, W, False), kblocks)
-        return bn % 32 == 0 and bn <= 192  # two bn x 256 B tile slots + >= 3 pipeline stages must fit in 227 KB
+        mt = ops.m_tiles(B, H, W, False)
+        bn = ops.pick_bn(cout, mt, kblocks)
+        if bn % 32 != 0 or bn > 192:  # two bn x 256 B tile slots + >= 3 pipeline stages must fit in 227 KB
+            return False
+        # mirror of evc_gemm_plan_create: a CTA must never own a third tile of a sample whose statistics it waits for
+        return ops.gn_fuse_fits((W // tw) * (H // th), mt, cout // bn)
 
     def ensure_stats(self, a):
         if a.stats is not None:
@@ -247,6 +267,13 @@ class EngineBase:
         else:
             self._op(lambda li: plan.launch(bias_fn(li)), "gemm", meta)
         return plan
+
+    def final_conv(self, segs, w, bias, c_out, H):
+        """Last conv: NHWC bf16 -> eps (B, c_out, H, H) fp32 NCHW, written by the epilogue directly (transposed fp32
+        store).  forward(eps_out=...) redirects it, e.g. into a slot of the F-PNDM eps history ring."""
+        self._eps_out = None
+        plan = self.gemm(segs, w, self.eps, EVC_OUT_F32_T, H * H, out_bs=c_out * H * H, bias=bias)
+        self.ops[-1] = lambda li, plan=plan: plan.launch(out=self._eps_out)
 
     def gn_fir(self, xa, xb, ss_fn, eps, adagn, up):
         """Fused prologue of an up / down res block: returns (FIR(SiLU(GN([xa|xb]))), [FIR(xa), FIR(xb)])."""
@@ -381,12 +408,18 @@ class EngineBase:
                 self.ops[idx] = (lambda li, plan=plan, bf=bias_fn: plan.launch(bf(li)))
         self._deferred = []
 
-    def forward(self, label_idx=0):
-        """Enqueue one UNet evaluation: reads self.xin, writes self.eps (B, C_out, H, W) fp32."""
+    def forward(self, label_idx=0, eps_out=None):
+        """Enqueue one UNet evaluation: reads self.xin, writes self.eps (B, C_out, H, W) fp32 -- or `eps_out`, a
+        contiguous fp32 tensor of the same shape (not available in split-precision mode)."""
+        if eps_out is not None:
+            if self.split or eps_out.shape != self.eps.shape or eps_out.dtype != torch.float32 or not eps_out.is_contiguous():
+                raise EvcError("eps_out must be a contiguous fp32 tensor shaped like eps (bf16 mode only)")
+        self._eps_out = eps_out
         ops.fill_zero(self.stats_arena)  # fused statistics accumulate with integer atomics
         for fn in self.ops:
             fn(label_idx)
-        return self.eps
+        self._eps_out = None
+        return self.eps if eps_out is None else eps_out
 
     def profile(self, label_idx=0, reps=3):
         """Per-launch device time of one UNet evaluation (CUDA events around every launch, eager mode).
@@ -421,7 +454,8 @@ class NCSNppEngine(EngineBase):
         self.head_ch = getattr(m, "n_head_channels", -1)
         if self.nf % 8 != 0:
             raise EvcError("evcdiff CUDA path needs model.ngf % 8 == 0 (16-byte channel vectors; % 64 for full speed)")
-        if self.c_x + self.c_cond > CIN_PAD:
+        self.c_cond_off = cond_offset(self.c_x)
+        if self.c_cond_off + self.c_cond > CIN_PAD:
             raise EvcError("more than 64 input channels is not supported")
         sd = {k: v.detach() for k, v in net.state_dict().items()}
         self.sd = sd
@@ -474,7 +508,7 @@ class NCSNppEngine(EngineBase):
         attn_res = list(m.attn_resolutions)
         i = 2
         h0 = self.new_act(H, H, spec[i]["cout"], scratch=False)
-        self.gemm([(xin, 9)], pack_conv3(sd[P(i) + ".weight"].to(dev), CIN_PAD), h0.t, EVC_OUT_BF16_ROWS, h0.C,
+        self.gemm([(xin, 9)], pack_conv_in(sd[P(i) + ".weight"].to(dev), self.c_x, CIN_PAD), h0.t, EVC_OUT_BF16_ROWS, h0.C,
                   bias=self.f32(P(i) + ".bias"), stats_of=h0)
         self.taps["m2"] = h0
         i += 1
@@ -512,8 +546,7 @@ class NCSNppEngine(EngineBase):
         self.gn_apply(h, None, lambda li: ss, 1e-5, False, True, hn)
         self.taps[f"m{i}"] = hn
         i += 1
-        self.gemm([(hn, 9)], pack_conv3(sd[P(i) + ".weight"].to(dev)), self.eps, EVC_OUT_F32_T, H * H,
-                  out_bs=self.c_x * H * H, bias=self.f32(P(i) + ".bias"))
+        self.final_conv([(hn, 9)], pack_conv3(sd[P(i) + ".weight"].to(dev)), self.f32(P(i) + ".bias"), self.c_x, H)
         i += 1
         assert i == len(spec)
 
@@ -614,7 +647,7 @@ class NCSNppEngine(EngineBase):
         ncsnpp_more.py:256-257 + the fp32 cast of :293, fused with the layout change)."""
         ops.pack_nchw(x.contiguous(), self.xin, 0, dst_lo=self.xin_lo)
         if cond is not None:
-            ops.pack_nchw(cond.contiguous(), self.xin, self.c_x, dst_lo=self.xin_lo)
+            ops.pack_nchw(cond.contiguous(), self.xin, self.c_cond_off, dst_lo=self.xin_lo)
 
     def refresh_x(self, x):
         """Split-precision mode: the sampler-update kernels only write the bf16 hi plane of x_t; rewrite both planes."""

@@ -14,7 +14,7 @@ import torch
 
 from . import ops
 from ._lib import EVC_OUT_BF16_ROWS, EVC_OUT_F32_T, EvcError
-from .engine import CIN_PAD, Act, EngineBase, pack_conv3
+from .engine import CIN_PAD, Act, EngineBase, cond_offset, pack_conv3, pack_conv_in
 
 
 class PlainUNetEngine(EngineBase):
@@ -31,7 +31,8 @@ class PlainUNetEngine(EngineBase):
         self.c_cond = d.channels * (d.num_frames_cond + getattr(d, "num_frames_future", 0))
         if self.ch % 32 != 0:
             raise EvcError("models/unet.py uses GroupNorm(32): model.ngf must be a multiple of 32")
-        if self.c_x + self.c_cond > CIN_PAD:
+        self.c_cond_off = cond_offset(self.c_x)
+        if self.c_cond_off + self.c_cond > CIN_PAD:
             raise EvcError("more than 64 input channels is not supported")
         self.sd = {k: v.detach() for k, v in net.state_dict().items()}
         self._build()
@@ -89,7 +90,7 @@ class PlainUNetEngine(EngineBase):
             else:
                 st = s["stride"]
                 out = self.new_act(x.H // st, x.W // st, s["cout"], scratch=False)
-                w = pack_conv3(sd[p + ".weight"].to(dev), CIN_PAD if j == 0 else None)
+                w = pack_conv_in(sd[p + ".weight"].to(dev), self.c_x, CIN_PAD) if j == 0 else pack_conv3(sd[p + ".weight"].to(dev))
                 self.gemm([(x, 9)], w, out.t, EVC_OUT_BF16_ROWS, s["cout"], bias=self.f32(p + ".bias"), stats_of=out,
                           stride=st)
                 x = out
@@ -122,8 +123,7 @@ class PlainUNetEngine(EngineBase):
         ss = self._gn_ss("normalize")
         hn = self.new_act(x.H, x.W, x.C)
         self.gn_apply(x, None, lambda li: ss, 1e-6, False, True, hn)
-        self.gemm([(hn, 9)], pack_conv3(sd["out.weight"].to(dev)), self.eps, EVC_OUT_F32_T, H * H,
-                  out_bs=spec["n_out"] * H * H, bias=self.f32("out.bias"))
+        self.final_conv([(hn, 9)], pack_conv3(sd["out.weight"].to(dev)), self.f32("out.bias"), spec["n_out"], H)
 
     def res_block(self, p, s, xa, xb):
         """ResnetBlock (unet.py:66-97) on the virtual concat [xa | xb]."""
@@ -198,7 +198,7 @@ class PlainUNetEngine(EngineBase):
     def load_input(self, x, cond):
         ops.pack_nchw(x.contiguous(), self.xin, 0, dst_lo=self.xin_lo)
         if cond is not None:
-            ops.pack_nchw(cond.contiguous(), self.xin, self.c_x, dst_lo=self.xin_lo)
+            ops.pack_nchw(cond.contiguous(), self.xin, self.c_cond_off, dst_lo=self.xin_lo)
 
     def refresh_x(self, x):
         if self.split:

@@ -14,9 +14,11 @@ Behaviour kept from the reference (quirks included):
   * `final_only=True` returns `x.unsqueeze(0)`; otherwise the per-step `x.to('cpu')` stack;
   * unknown keyword arguments are swallowed.
 Not supported (raise, no fallback): gamma noise, t_min > 0 (noised-start), frac_steps.
-Extra optional keywords: `noise` (sequence / tensor of per-step noise, used instead of the generator -- parity
-tests feed the oracle's noise through it), `graph` (False = eager launches, default True) and `precision`
-('bf16' default | 'fp32': split-bf16 x3 tensor-core arithmetic, per-step x_t within 1e-3 of the fp32 reference).
+Extra optional keywords: `noise` (sequence / tensor of per-step noise, used instead of the generator: parity tests
+feed the oracle's noise through it, and the multi-GPU path feeds each rank its slice of the global-batch noise;
+with graph=True it is copied into a static tape the captured graph reads), `graph` (False = eager launches,
+default True) and `precision` ('bf16' = the model's default | 'fp32': split-bf16 x3 tensor-core arithmetic, per-step
+x_t within 1e-3 of the fp32 reference; applies to this call only).
 """
 import numpy as np
 import torch
@@ -77,8 +79,6 @@ def _unsupported(gamma, t_min, frac_steps=None):
 def _ancestral(kind, x_mod, scorenet, cond, final_only, denoise, subsample_steps, clip_before, just_beta, same_noise,
                noise_val, noise, graph, precision=None):
     net = _net_of(scorenet)
-    if precision is not None:
-        net.precision = precision
     steps, alphas, alphas_prev, betas = _subsampled_schedule(net, subsample_steps)
     L = len(steps)
     # per-step coefficients, evaluated with the same fp32 tensor expressions as the reference
@@ -95,22 +95,24 @@ def _ancestral(kind, x_mod, scorenet, cond, final_only, denoise, subsample_steps
         c_eps = (1 - alphas_prev).sqrt()
         c_noise = torch.zeros_like(alphas)
     tab = torch.stack([k0, k1, c_x0, c_x, c_eps, c_noise], 1).float().cpu().tolist()
-    coefs, labels = [], []
+    coefs, labels, draws = [], [], []
     for i in range(L):
         r = tab[i]
-        use_noise = kind == "ddpm" and (i + 1 != L)
+        use_noise = kind == "ddpm" and (i + 1 != L)  # the reference draws on every non-final step (:313-326)
         coefs.append(StepCoef(0, int(bool(clip_before)), r[0], r[1], r[2], r[3], r[4], r[5] if use_noise else 0.0))
         labels.append(float(steps[i]))
+        draws.append(use_noise)
     if denoise:
         coefs.append(StepCoef(1, 0, 0.0, tab[-1][1], 0.0, 0.0, 0.0, 0.0))
         labels.append(float(L - 1))
+        draws.append(False)
     if same_noise and noise_val is None:
         noise_val = x_mod.detach().clone()
-    loop = SamplerLoop.get(net, x_mod.shape[0], x_mod.device)
+    loop = SamplerLoop.get(net, x_mod.shape[0], x_mod.device, precision)  # precision: this call only (None = net.precision)
     key = (kind, L, int(bool(denoise)), int(bool(clip_before)), int(bool(just_beta)), tuple(labels),
            tuple(c.c_noise for c in coefs))
     return loop.run_ancestral(key, x_mod, cond, labels, coefs, final_only=final_only, noise=noise,
-                              noise_const=noise_val if same_noise else None, graph=graph)
+                              noise_const=noise_val if same_noise else None, graph=graph, draws=draws)
 
 
 @torch.no_grad()
@@ -137,14 +139,12 @@ def FPNDM_sampler(x_mod, scorenet, cond=None, final_only=False, denoise=True, su
                   log=True, clip_before=True, t_min=-1, gamma=False, graph=True, precision=None, **kwargs):
     """F-PNDM sampling: 3 Runge-Kutta steps then 4th-order Adams-Bashforth (reference models/__init__.py:39-100)."""
     net = _net_of(scorenet)
-    if precision is not None:
-        net.precision = precision
     alphas = net.alphas
     skip = len(alphas) // subsample_steps  # TypeError on None, like the reference (:62)
     steps = list(range(0, len(alphas), skip))
     steps_next = [-1] + steps[:-1]
     alphas_old = alphas.flip(0).float().cpu()
-    loop = SamplerLoop.get(net, x_mod.shape[0], x_mod.device)
+    loop = SamplerLoop.get(net, x_mod.shape[0], x_mod.device, precision)
     key = ("fpndm", len(steps), skip, int(bool(clip_before)))
     return loop.run_fpndm(key, x_mod, cond, steps, steps_next, alphas_old, clip_before, final_only=final_only,
                           graph=graph)

@@ -1,7 +1,8 @@
 """EMA shadow weights with the reference's interface (reference models/ema.py:4-47): the sender loads the
 checkpoint's EMA dict with `load_state_dict` and copies it into the model with `ema` (city_sender.py:317-322).
-Pure parameter bookkeeping (no kernels); the engine notices the in-place `copy_` through the parameters'
-version counters and repacks its bf16 operands before the next sampling call."""
+Pure parameter bookkeeping (no kernels).  `ema()` copies with `p.copy_()` under no_grad (which bumps the version
+counter the engines watch; `p.data.copy_()` would not) and also bumps the model's explicit weights epoch, so the
+bf16 operands are repacked before the next sampling call."""
 import torch
 import torch.nn as nn
 
@@ -31,7 +32,11 @@ class EMAHelper(object):
     @torch.no_grad()
     def ema(self, module):
         for n, p in _trainable(module):
-            p.data.copy_(self.shadow[n])  # in place: bumps the version counter the engine watches
+            p.copy_(self.shadow[n])  # in place on the parameter itself: bumps p._version (p.data.copy_ does not)
+        inner = module.module if isinstance(module, nn.DataParallel) else module
+        for m in inner.modules():  # engines also compare an explicit epoch (robust against `.data` edits made by callers)
+            if hasattr(m, "_weights_epoch"):
+                m._weights_epoch += 1
 
     def ema_copy(self, module):
         wrapped = isinstance(module, nn.DataParallel)

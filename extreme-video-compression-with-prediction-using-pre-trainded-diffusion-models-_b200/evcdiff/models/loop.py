@@ -16,11 +16,11 @@ from .._lib import EvcError, PndmCoef
 
 class SamplerLoop:
     @staticmethod
-    def get(net, B, device):
+    def get(net, B, device, precision=None):
         device = torch.device(device)
         if device.type != "cuda":
             raise EvcError("evcdiff samplers need CUDA tensors (no CPU fallback)")
-        eng = net.engine(B, device)
+        eng = net.engine(B, device, precision=precision)
         loop = getattr(eng, "_loop", None)
         if loop is None:
             loop = SamplerLoop(net, eng)
@@ -35,6 +35,7 @@ class SamplerLoop:
         self.noise = torch.zeros(shape, dtype=torch.float32, device=dev)
         self.e = None
         self.scratch = None
+        self.tape = None  # static per-step noise tape (caller-supplied noise inside a captured graph)
         self.graphs = {}
         self.launches_per_run = {}
 
@@ -95,27 +96,63 @@ class SamplerLoop:
         self.scratch.copy_(self.eng.eps)
 
     # ------------------------------------------------------------------------------------------
-    def run_ancestral(self, key, x_mod, cond, labels, coefs, final_only, noise=None, noise_const=None, graph=True):
+    def _check_noise(self, t, what):
+        """Caller-supplied noise must be exactly what the kernel reads: fp32, contiguous, the shape of x, on this device."""
+        if not torch.is_tensor(t):
+            raise EvcError(f"{what} must be a tensor")
+        if tuple(t.shape) != tuple(self.x.shape):
+            raise EvcError(f"{what} has shape {tuple(t.shape)}, expected {tuple(self.x.shape)}")
+        return t.to(self.x.device, torch.float32).contiguous()
+
+    def run_ancestral(self, key, x_mod, cond, labels, coefs, final_only, noise=None, noise_const=None, graph=True,
+                      draws=None):
+        """draws[i]: does step i consume one Gaussian draw (the reference draws `randn_like` on every non-final DDPM
+        step, models/__init__.py:313-326, whatever the value of the coefficient)."""
+        with torch.cuda.device(self.eng.device):
+            return self._run_ancestral(key, x_mod, cond, labels, coefs, final_only, noise, noise_const, graph, draws)
+
+    def _run_ancestral(self, key, x_mod, cond, labels, coefs, final_only, noise, noise_const, graph, draws):
         eng = self.eng
+        if draws is None:
+            draws = [c.mode == 0 and c.c_noise != 0.0 for c in coefs]
+        n_draws = sum(1 for d in draws if d)
         uniq = list(dict.fromkeys(labels))
         idx = [uniq.index(v) for v in labels]
         eng.set_labels(uniq)
         self._load(x_mod, cond)
         images = []
-        ext_noise = noise is not None or noise_const is not None
-        if ext_noise or not final_only:
+        if noise_const is not None:
+            noise_const = self._check_noise(noise_const, "noise_val")
+        if not final_only:
             graph = False  # per-step host interaction: eager launches
+        tape = None
+        if noise is not None and noise_const is None:
+            if len(noise) < n_draws:
+                raise EvcError(f"noise has {len(noise)} entries, the schedule draws {n_draws}")
+            if graph:
+                # static tape: the captured graph reads slot i at the i-th draw; contents are refreshed before each replay
+                if self.tape is None or self.tape.shape[0] < n_draws:
+                    self.tape = torch.empty((n_draws,) + tuple(self.x.shape), dtype=torch.float32, device=self.x.device)
+                for i in range(n_draws):
+                    self.tape[i].copy_(self._check_noise(noise[i], f"noise[{i}]"))
+                tape = self.tape
+                key = key + ("tape", self.tape.data_ptr())
+            else:
+                tape = [self._check_noise(noise[i], f"noise[{i}]") for i in range(n_draws)]
+        elif noise_const is not None:
+            key = key + ("const", noise_const.data_ptr())
+            graph = False
 
         def body():
             ni = 0
             for i, c in enumerate(coefs):
                 eng.forward(idx[i])
                 nz = None
-                if c.mode == 0 and c.c_noise != 0.0:
+                if draws[i]:
                     if noise_const is not None:
                         nz = noise_const
-                    elif noise is not None:
-                        nz = noise[ni].to(self.x.device, torch.float32).contiguous()
+                    elif tape is not None:
+                        nz = tape[ni]
                         ni += 1
                     else:
                         self.noise.normal_()
@@ -133,6 +170,10 @@ class SamplerLoop:
     # ------------------------------------------------------------------------------------------
     def run_fpndm(self, key, x_mod, cond, steps, steps_next, alphas_old, clip_before, final_only, graph=True):
         """F-PNDM (reference models/__init__.py:79-100 + models/pndm.py:3-52)."""
+        with torch.cuda.device(self.eng.device):
+            return self._run_fpndm(key, x_mod, cond, steps, steps_next, alphas_old, clip_before, final_only, graph)
+
+    def _run_fpndm(self, key, x_mod, cond, steps, steps_next, alphas_old, clip_before, final_only, graph):
         eng = self.eng
         if self.e is None:
             self.e = [torch.zeros_like(self.x) for _ in range(7)]  # ring of 4 + 3 Runge-Kutta stages
@@ -168,6 +209,15 @@ class SamplerLoop:
             c.d, c.p, c.q = float(d), float(p), float(q)
             return c
 
+        def evaluate(label_idx, dst):
+            """eps of the current UNet input -> dst: the final conv's epilogue writes the history slot directly (bf16
+            mode); split-precision mode keeps the engine's own eps buffer and copies."""
+            if eng.split:
+                eng.forward(label_idx)
+                dst.copy_(eng.eps)
+            else:
+                eng.forward(label_idx, eps_out=dst)
+
         def body():
             ring = []  # eps history buffers, most recent last
             free = list(self.e)
@@ -176,8 +226,7 @@ class SamplerLoop:
                     free.append(ring.pop(0))
                 e1 = free.pop()
                 if kind == "ab":
-                    eng.forward(li[t])
-                    e1.copy_(eng.eps)
+                    evaluate(li[t], e1)
                     ring.append(e1)
                     es = [ring[-1], ring[-2], ring[-3], ring[-4]]
                     ops.pndm_update(self.x, es, self.x, None, eng.xin, coef(t, tn, 4, (55.0, -59.0, 37.0, -9.0), 1 / 24))
@@ -185,17 +234,17 @@ class SamplerLoop:
                 else:
                     tm = (t + tn) / 2
                     e2, e3, e4 = free[-1], free[-2], free[-3]
-                    eng.forward(li[t]); e1.copy_(eng.eps)
+                    evaluate(li[t], e1)
                     ring.append(e1)
                     ops.pndm_update(self.x, [e1], self.scratch, None, eng.xin, coef(t, tm, 1, (1.0,), 1.0))
                     eng.refresh_x(self.scratch)
-                    eng.forward(li[tm]); e2.copy_(eng.eps)
+                    evaluate(li[tm], e2)
                     ops.pndm_update(self.x, [e2], self.scratch, None, eng.xin, coef(t, tm, 1, (1.0,), 1.0))
                     eng.refresh_x(self.scratch)
-                    eng.forward(li[tm]); e3.copy_(eng.eps)
+                    evaluate(li[tm], e3)
                     ops.pndm_update(self.x, [e3], self.scratch, None, eng.xin, coef(t, tn, 1, (1.0,), 1.0))
                     eng.refresh_x(self.scratch)
-                    eng.forward(li[tn]); e4.copy_(eng.eps)
+                    evaluate(li[tn], e4)
                     ops.pndm_update(self.x, [e1, e2, e3, e4], self.x, None, eng.xin,
                                     coef(t, tn, 4, (1.0, 2.0, 2.0, 1.0), 1 / 6))
                     eng.refresh_x(self.x)

@@ -147,24 +147,33 @@ class UNet(nn.Module):
         default_init(self.temb_dense[0], 1)
         default_init(self.temb_dense[2], 1)
         self._engines = {}
+        self._weights_epoch = 0  # bumped by EMAHelper.ema / mark_weights_changed(); part of the engines' staleness key
         # 'bf16' (default, tensor-core speed) or 'fp32' (split-bf16 x3: per-step x_t within 1e-3 of the fp32 reference)
         self.precision = os.environ.get("EVC_PRECISION", getattr(config, "precision", "bf16"))
 
     def _weights_version(self):
-        return sum(p._version for p in self.parameters()) + 7919 * sum(p.data_ptr() % 65521 for p in self.parameters())
+        return (self._weights_epoch, sum(p._version for p in self.parameters()),
+                sum(p.data_ptr() % 65521 for p in self.parameters()))
 
-    def engine(self, B, device=None):
+    def mark_weights_changed(self):
+        """Call after editing parameters in a way autograd's version counters do not see (e.g. `p.data.copy_()`)."""
+        self._weights_epoch += 1
+
+    def engine(self, B, device=None, precision=None):
+        """The launch plan for batch size B; `precision` overrides self.precision for this lookup only."""
         from ..engine_unet import PlainUNetEngine
         device = torch.device(device) if device is not None else next(self.parameters()).device
         if device.type != "cuda":
             raise EvcError("evcdiff runs on CUDA devices only; move the model with .to('cuda')")
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        key, ver = (B, str(device), self.precision), self._weights_version()
+        precision = precision or self.precision
+        key, ver = (B, str(device), precision), self._weights_version()
         hit = self._engines.get(key)
         if hit is None or hit[0] != ver:
             self._engines.pop(key, None)
-            hit = (ver, PlainUNetEngine(self, B, device, self.precision))
+            with torch.cuda.device(device):
+                hit = (ver, PlainUNetEngine(self, B, device, precision))
             self._engines[key] = hit
         return hit[1]
 
@@ -176,9 +185,10 @@ class UNet(nn.Module):
         if not bool((lab == v).all()):
             raise EvcError("per-sample labels are not supported: the sampling path uses batch-uniform labels")
         eng = self.engine(x.shape[0], x.device)
-        eng.set_labels([v])
-        eng.load_input(x, cond)
-        return eng.forward(0).clone()
+        with torch.cuda.device(eng.device):
+            eng.set_labels([v])
+            eng.load_input(x, cond)
+            return eng.forward(0).clone()
 
 
 class UNet_DDPM(nn.Module):
@@ -211,8 +221,8 @@ class UNet_DDPM(nn.Module):
     def precision(self, value):
         self.unet.precision = value
 
-    def engine(self, B, device=None):
-        return self.unet.engine(B, device)
+    def engine(self, B, device=None, precision=None):
+        return self.unet.engine(B, device, precision)
 
     def forward(self, x, y, cond=None, labels=None, cond_mask=None):
         return self.unet(x, y, cond)

@@ -108,12 +108,13 @@ class GemmPlan:
         self.flops = lib.evc_gemm_plan_flops(h)
         self.cta_group = lib.evc_gemm_plan_cta_group(h)
 
-    def launch(self, bias_override=None, gn_ss=None):
-        if gn_ss is None:
+    def launch(self, bias_override=None, gn_ss=None, out=None):
+        """out: redirect a per-thread-store output (fp32 / transposed modes) to another tensor of the same layout."""
+        if gn_ss is None and out is None:
             check(self._lib.evc_gemm_plan_launch(self._h, _ptr(bias_override), stream_ptr()), "evc_gemm_plan_launch")
         else:
-            check(self._lib.evc_gemm_plan_launch_gn(self._h, _ptr(bias_override), _ptr(gn_ss), stream_ptr()),
-                  "evc_gemm_plan_launch_gn")
+            check(self._lib.evc_gemm_plan_launch_ex(self._h, _ptr(bias_override), _ptr(gn_ss), _ptr(out), stream_ptr()),
+                  "evc_gemm_plan_launch_ex")
 
     def __del__(self):
         try:
@@ -189,6 +190,30 @@ def pick_bn(n, mt=None, kblocks=None, sms=148):
         if best_cost is None or cost < best_cost * 0.97:  # prefer wider tiles unless clearly slower
             best, best_cost = bn, cost
     return best
+
+
+def gn_fuse_fits(sample_m_tiles, m_tiles_total, tiles_n, sms=None):
+    """Host mirror of the fused-GroupNorm-apply guard in evc_gemm_plan_create (gemm_tc.cu): the tiles of one sample must
+    fit in two rounds of the persistent grid, otherwise a CTA would wait for a tile it owns itself."""
+    sms = sms or num_sms()
+    for cg in (1, 2):  # whichever grouping the plan picks (conservative: both must fit)
+        cap = max(1, sms // cg)
+        units_total = ((m_tiles_total + cg - 1) // cg) * tiles_n
+        num_units = min(units_total, cap)
+        sample_units = ((sample_m_tiles + cg - 1) // cg) * tiles_n + (tiles_n if cg > 1 else 0)
+        if sample_units > 2 * num_units:
+            return False
+    return True
+
+
+_sms = {}
+
+
+def num_sms():
+    dev = torch.cuda.current_device()
+    if dev not in _sms:
+        _sms[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return _sms[dev]
 
 
 def gn_stats_workspace_bytes(B, HW, Cc):
@@ -316,6 +341,16 @@ def pndm_update(x, eps_list, x_out, et_out, xin, coef: PndmCoef):
 def inverse_transform(x, frames):
     _require_cuda(x, frames)
     check(load().evc_inverse_transform(_ptr(x), _ptr(frames), x.numel(), stream_ptr()), "evc_inverse_transform")
+
+
+def frames_to_uint8(frames, out):
+    _require_cuda(frames, out)
+    assert frames.dtype == torch.float32 and out.dtype == torch.uint8 and frames.numel() == out.numel()
+    check(load().evc_frames_to_uint8(_ptr(frames), _ptr(out), frames.numel(), stream_ptr()), "evc_frames_to_uint8")
+
+
+def gemm_fault_count():
+    return int(load().evc_gemm_fault_count())
 
 
 def frame_psnr(a, b, maxvalue=1.0):

@@ -138,6 +138,14 @@ int evc_gemm_plan_launch(const evc_gemm_plan* plan, const float* bias_override, 
 /* same, with the [gamma' | beta'] row of the current label for a plan created with gn_ss (NULL = desc->gn_ss) */
 int evc_gemm_plan_launch_gn(const evc_gemm_plan* plan, const float* bias_override, const float* gn_ss_override,
                             evc_stream_t stream);
+/* General form: out_override (NULL = desc->out) redirects a per-thread-store output (fp32 / transposed modes, e.g. the
+ * final conv writing eps straight into a slot of the F-PNDM history ring, models/pndm.py:41-52) -- not valid for
+ * plans that store through TMA (bf16 row outputs of whole tiles), whose descriptors hold the pointer. */
+int evc_gemm_plan_launch_ex(const evc_gemm_plan* plan, const float* bias_override, const float* gn_ss_override,
+                            void* out_override, evc_stream_t stream);
+/* Synchronising debug query (not capturable): tile waits of the fused GroupNorm apply that gave up since the last
+ * call. 0 unless a caller launched a gn_ss plan without zeroing gn_ticket; -1 without a device. */
+int64_t evc_gemm_fault_count(void);
 void evc_gemm_plan_destroy(evc_gemm_plan* plan);
 /* 2 * M * N * K of one launch (dense FLOPs, for the roofline) */
 double evc_gemm_plan_flops(const evc_gemm_plan* plan);
@@ -248,8 +256,11 @@ int evc_fill_zero(void* p, int64_t bytes, evc_stream_t stream);
 /* One sampler update, NCHW fp32 state (models/__init__.py:289-335 ddpm, :166-169 ddim, :196/:333-335 denoise):
  *   mode 0:  x0 = k0*(x - k1*eps); if clip: x0 = clamp(x0,-1,1);  x' = c_x0*x0 + c_x*x + c_eps*eps + c_noise*noise
  *   mode 1:  x' = x - k1*eps                                    (final denoise)
- * also writes bf16(x') into channels [0,C) of the NHWC UNet input `xin` (row stride Cpad). noise may be NULL
- * when c_noise == 0. x_out may alias x. */
+ * also writes bf16(x') into the NHWC UNet input `xin` (row stride Cpad, Cpad % 8 == 0): channels [0, CP) with
+ * CP = C rounded up to 8 -- whole 16-byte chunks, the pad channels [C, CP) are written as zero, so the conditioning
+ * frames of the virtual torch.cat (ncsnpp_more.py:256-257) live at channel CP onwards and the first conv's weight has
+ * zero columns for the pad channels. noise may be NULL when c_noise == 0. x_out may alias x. Vectorised (float4
+ * planes, 4 pixels per thread) when HW % 4 == 0 and all pointers are 16-byte aligned. */
 typedef struct evc_step_coef {
   int32_t mode, clip;
   float k0, k1, c_x0, c_x, c_eps, c_noise;
@@ -271,6 +282,9 @@ int evc_pndm_update(const float* x, const float* const* e_host, float* x_out, fl
 
 /* frames = clamp((x+1)/2, 0, 1), NCHW fp32 -> NCHW fp32 (inverse_data_transform, function.py:73-82) */
 int evc_inverse_transform(const float* x, float* frames, int64_t n, evc_stream_t stream);
+/* out = uint8(round(255 * frames)) -- the storage format of the data set (city_sender.py:487 divides it by 255);
+ * used for the end-of-run gather of predicted frames (4x less NVLink traffic than fp32). */
+int evc_frames_to_uint8(const float* frames, uint8_t* out, int64_t n, evc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sender-side accept decision on the GPU (next rows of the path): per-frame PSNR in float64

@@ -37,6 +37,66 @@ def _worker(rank, world, port, n_videos, out):
     dist.destroy_process_group()
 
 
+def _fake_frames(net, input_frames, config=None, sampler="DDPM", init_samples=None, noise=None, to_host=False,
+                 max_batch=64, **kw):
+    """Stand-in for pipeline.generate_frame with the same signature: any per-video function of (cond, x_T, noise)."""
+    x = init_samples + 0.25 * input_frames.float().mean(dim=1, keepdim=True)
+    for n in (noise or []):
+        x = torch.tanh(x + 0.1 * n)
+    return x.reshape(x.shape[0], config.data.num_frames, config.data.channels, *x.shape[-2:])
+
+
+def _sharded_worker(rank, world, port, n_videos, sampler, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from evcdiff import pipeline
+    cfg = common.make_config(image_size=8)
+    cfg.sampling.subsample = 5
+    g = torch.Generator().manual_seed(7)
+    frames01 = torch.rand(n_videos, 6, 8, 8, generator=g, dtype=torch.float64)
+    got = pipeline.generate_frame_sharded(torch.nn.Linear(1, 1), frames01, rank, world, config=cfg, sampler=sampler,
+                                          seed=1234, frame_fn=_fake_frames, gather="fp32")
+    got8 = pipeline.generate_frame_sharded(torch.nn.Linear(1, 1), frames01, rank, world, config=cfg, sampler=sampler,
+                                           seed=1234, frame_fn=lambda *a, **k: torch.sigmoid(_fake_frames(*a, **k)),
+                                           gather="uint8")
+    if rank == 0:
+        ref = pipeline.generate_frame_sharded(torch.nn.Linear(1, 1), frames01, 0, 1, config=cfg, sampler=sampler,
+                                              seed=1234, frame_fn=_fake_frames)
+        torch.save({"got": got, "ref": ref, "got8": got8}, out)
+    else:
+        assert got is None and got8 is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_generate_frame_sharded_two_ranks_equals_one(tmp_path):
+    """The real host logic of the multi-GPU path (pipeline.generate_frame_sharded: global-seed draws sliced per rank,
+    uneven shards padded for the gather, fp32 and uint8 gathers) with a stand-in for the CUDA sampler."""
+    for i, (n, sampler) in enumerate([(5, "DDPM"), (1, "DDPM"), (4, "FPNDM")]):
+        out = str(tmp_path / f"res{i}.pt")
+        port = 29600 + (os.getpid() % 2000) + i
+        mp.spawn(_sharded_worker, args=(2, port, n, sampler, out), nprocs=2, join=True)
+        res = torch.load(out)
+        assert res["got"].shape == (n, 5, 3, 8, 8)
+        assert torch.equal(res["got"], res["ref"])
+        assert res["got8"].dtype == torch.uint8 and res["got8"].shape == (n, 5, 3, 8, 8)
+        assert torch.equal(res["got8"], (torch.sigmoid(res["ref"]) * 255).round().to(torch.uint8))
+
+
+def test_global_draws_match_reference_rng_order():
+    """x_T first, then one draw per non-final DDPM step, from one generator: the order of city_sender.py:330-333 and
+    models/__init__.py:326; DDIM / F-PNDM draw no step noise."""
+    from evcdiff import pipeline
+    cfg = common.make_config(image_size=8)
+    x_T, noise = pipeline.global_draws(3, cfg, "DDPM", 10, 99, "cpu")
+    g = torch.Generator().manual_seed(99)
+    assert torch.equal(x_T, torch.randn(3, 15, 8, 8, generator=g))
+    assert len(noise) == 9 and torch.equal(noise[0], torch.randn(3, 15, 8, 8, generator=g))
+    assert pipeline.global_draws(3, cfg, "DDIM", 10, 99, "cpu")[1] is None
+    assert len(pipeline.global_draws(2, cfg, "DDPM", None, 1, "cpu")[1]) == 999
+
+
 def test_shard_ranges():
     from evcdiff.pipeline import shard_range
     assert [shard_range(46, r, 8) for r in range(8)] == [(0, 6), (6, 12), (12, 18), (18, 24), (24, 30), (30, 36),

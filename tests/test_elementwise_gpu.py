@@ -177,7 +177,7 @@ def test_sampler_updates_match_oracle_arithmetic():
     x = torch.randn(2, 15, 16, 16, device=DEV, generator=g)
     e = torch.randn(2, 15, 16, 16, device=DEV, generator=g)
     nz = torch.randn(2, 15, 16, 16, device=DEV, generator=g)
-    xin = torch.zeros(2, 16, 16, 64, device=DEV, dtype=torch.bfloat16)
+    xin = torch.full((2, 16, 16, 64), 7.0, device=DEV, dtype=torch.bfloat16)
     for i in (0, 37, 98):
         ca, cap, cb = a[i], ap[i], b[i]
         x0 = ((1 / ca.sqrt()) * (x - (1 - ca).sqrt() * e)).clip_(-1, 1)
@@ -190,6 +190,8 @@ def test_sampler_updates_match_oracle_arithmetic():
         torch.cuda.synchronize()
         assert common.rel_l2(out, ref) < 1e-6
         assert torch.equal(nchw(xin)[:, :15], out.bfloat16().float())
+        # whole 16-byte chunks: the pad channel 15 is written as zero, the conditioning channels (16..) are untouched
+        assert bool((nchw(xin)[:, 15] == 0).all()) and bool((nchw(xin)[:, 16:] == 7.0).all())
         # DDIM
         ref = cap.sqrt() * x0 + (1 - cap).sqrt() * e
         c = StepCoef(0, 1, float(1 / ca.sqrt()), float((1 - ca).sqrt()), float(cap.sqrt()), 0.0, float((1 - cap).sqrt()), 0.0)
@@ -216,6 +218,86 @@ def test_sampler_updates_match_oracle_arithmetic():
     got = pndm._combine(es, (55.0, -59.0, 37.0, -9.0), 1 / 24)
     torch.cuda.synchronize()
     assert common.rel_l2(got, ref) < 1e-6
+
+
+def test_sampler_update_vector_and_scalar_paths_agree():
+    """The float4 / 4-pixels-per-thread kernels (HW % 4 == 0, aligned) and the scalar fallback (ragged HW, misaligned
+    views) compute bit-identical updates and write the same UNet-input rows; C = 15 and C = 9 (CP = 16)."""
+    ops = _ops()
+    from evcdiff._lib import PndmCoef, StepCoef
+    g = torch.Generator(device=DEV).manual_seed(41)
+    c = StepCoef(0, 1, 1.7, 0.6, 0.3, 0.65, 0.0, 0.2)
+    pc = PndmCoef()
+    pc.n_e, pc.clip, pc.w_scale, pc.d, pc.p, pc.q = 4, 1, 1 / 24, 0.05, 0.9, 1.3
+    for j, w in enumerate((55.0, -59.0, 37.0, -9.0)):
+        pc.w[j] = w
+    for C in (15, 9):
+        B, H, W = 3, 12, 12
+        al = [torch.randn(B, C, H, W, device=DEV, generator=g) for _ in range(7)]  # aligned planes -> vector path
+        x, e, nz = al[0], al[1], al[2]
+        xin_v = torch.full((B, H, W, 64), 3.0, device=DEV, dtype=torch.bfloat16)
+        out_v = torch.empty_like(x)
+        ops.sampler_update(x, e, nz, out_v, xin_v, c)
+        # misaligned copies of the same data (offset by one float) force the scalar kernel
+        xm, em, nm = [torch.empty(B * C * H * W + 1, device=DEV)[1:].view(B, C, H, W) for _ in range(3)]
+        xm.copy_(x); em.copy_(e); nm.copy_(nz)
+        xin_s = torch.full((B, H, W, 64), 3.0, device=DEV, dtype=torch.bfloat16)
+        out_s = torch.empty_like(x)
+        ops.sampler_update(xm, em, nm, out_s, xin_s, c)
+        torch.cuda.synchronize()
+        assert torch.equal(out_v, out_s) and torch.equal(xin_v, xin_s)
+        CP = (C + 7) // 8 * 8
+        assert bool((xin_v[..., C:CP] == 0).all()) and bool((xin_v[..., CP:] == 3.0).all())
+        assert torch.equal(xin_v[..., :C].float(), out_v.permute(0, 2, 3, 1).bfloat16().float())
+        # PNDM: 4-term multistep, et written out, in-place x
+        es = [al[3], al[4], al[5], al[6]]
+        xv, xs = x.clone(), xm.clone()
+        etv, ets = torch.empty_like(x), torch.empty_like(x)
+        ops.pndm_update(xv, es, xv, etv, xin_v, pc)
+        esm_v = [torch.empty(B * C * H * W + 1, device=DEV)[1:].view(B, C, H, W) for _ in range(4)]
+        for a_, b_ in zip(esm_v, es):
+            a_.copy_(b_)
+        ops.pndm_update(xs, esm_v, xs, ets, xin_s, pc)
+        torch.cuda.synchronize()
+        assert torch.equal(xv, xs) and torch.equal(etv, ets) and torch.equal(xin_v, xin_s)
+        ref_et = (1 / 24) * (55 * es[0] - 59 * es[1] + 37 * es[2] - 9 * es[3])
+        assert common.rel_l2(etv, ref_et) < 1e-6
+    # ragged H*W (not a multiple of 4): scalar path, against the tensor expression
+    x = torch.randn(2, 15, 3, 3, device=DEV, generator=g)
+    e = torch.randn(2, 15, 3, 3, device=DEV, generator=g)
+    out = torch.empty_like(x)
+    ops.sampler_update(x, e, None, out, None, StepCoef(1, 0, 0.0, 0.25, 0, 0, 0, 0))
+    torch.cuda.synchronize()
+    assert common.rel_l2(out, x - 0.25 * e) < 1e-7
+
+
+def test_frames_to_uint8_and_final_conv_redirect():
+    """uint8 frame format for the end-of-run gather (round half to even like torch.round) and the eps_out redirect of
+    the last conv (F-PNDM writes eps straight into its history ring)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(43)
+    fr = torch.rand(3, 5, 3, 16, 16, device=DEV, generator=g)
+    fr.view(-1)[:8] = torch.tensor([0.0, 1.0, 0.5 / 255, 1.5 / 255, 2.5 / 255, 254.5 / 255, 0.999, 0.001], device=DEV)
+    out = torch.empty(fr.shape, dtype=torch.uint8, device=DEV)
+    ops.frames_to_uint8(fr, out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, (fr * 255.0).round().clamp(0, 255).to(torch.uint8))
+    odd = torch.rand(1027, device=DEV, generator=g)
+    o2 = torch.empty(1027, dtype=torch.uint8, device=DEV)
+    ops.frames_to_uint8(odd, o2)
+    assert torch.equal(o2, (odd * 255.0).round().to(torch.uint8))
+    from evcdiff.models.better.ncsnpp_more import UNetMore_DDPM
+    cfg = common.gpu64_config(device=DEV)
+    net = UNetMore_DDPM(cfg).to(DEV).eval()
+    eng = net.engine(2, DEV)
+    eng.set_labels([100.0])
+    x = torch.randn(2, 15, 32, 32, device=DEV, generator=g)
+    eng.load_input(x, None)
+    a = eng.forward(0).clone()
+    dst = torch.full_like(a, float("nan"))
+    b = eng.forward(0, eps_out=dst)
+    torch.cuda.synchronize()
+    assert b is dst and torch.equal(a, dst)
 
 
 def _guarded(shape, dtype, fill):

@@ -137,16 +137,25 @@ def test_checkpoint_loading_flow_like_city_sender():
     states = [{"module." + k: v.clone() for k, v in src.state_dict().items()},
               {k: torch.full_like(p, 0.25) for k, p in src.named_parameters()}]
     scorenet = torch.nn.DataParallel(UNetMore_DDPM(cfg))
-    v0 = scorenet.module.unet._weights_version()
+    v_init = scorenet.module.unet._weights_version()
     scorenet.load_state_dict(states[0], strict=False)
     scorenet.eval()
+    v0 = scorenet.module.unet._weights_version()  # read AFTER load_state_dict: ema() alone must change it
+    assert v0 != v_init
     ema_helper = EMAHelper(mu=cfg.model.ema_rate)
     ema_helper.register(scorenet)
     ema_helper.load_state_dict(states[-1])
     ema_helper.ema(scorenet)
     net = scorenet.module if hasattr(scorenet, "module") else scorenet
     assert all(bool((p == 0.25).all()) for p in net.parameters())
-    assert net.unet._weights_version() != v0  # the engine will repack its operands
+    v1 = net.unet._weights_version()
+    assert v1 != v0  # the engine will repack its operands
+    assert v1[1] != v0[1]  # ... through the parameters' own version counters, not only the explicit epoch
+    with torch.no_grad():
+        next(net.parameters()).data.mul_(2.0)  # invisible to version counters
+    assert net.unet._weights_version() == v1
+    net.unet.mark_weights_changed()
+    assert net.unet._weights_version() != v1
 
 
 def test_pipeline_get_model_loads_checkpoint_once():
@@ -201,6 +210,18 @@ def test_header_is_valid_c_and_links_from_a_c_host(tmp_path):
     assert "evcdiff ABI version 1" in out
 
 
+def test_bench_reference_arm_falls_back_to_port(monkeypatch):
+    """Without a reachable copy of the reference the arm times the oracle port and says so."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(bench, "REF_ROOTS", [None, "/nonexistent"])
+    assert bench.find_reference() is None
+    base = bench.cpu_baseline(1, one_thread=False)
+    assert base["kind"] == "port" and base["value"] > 0
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the reference's CPU path, timed on the host) prints one JSON line with the contract
     keys; it needs no GPU, so it runs here with a one-evaluation sample."""
@@ -214,6 +235,10 @@ def test_bench_reference_arm_contract():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # "reference" when an unmodified copy of the reference is reachable (baseline/_ref, installed by build() in the
+    # build container and shipped to the GPU box), else the oracle port
+    have_ref = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "models", "__init__.py")) or \
+        os.path.isdir("/root/reference/models") or bool(os.environ.get("EVC_REF"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"] and line["vs_baseline"] is None
