@@ -67,12 +67,16 @@ def test_eps_b46_every_sample(full, cta_group, monkeypatch):
         net.unet._engines.pop((46, str(torch.device("cuda", torch.cuda.current_device())), "bf16"), None)
         monkeypatch.delenv("EVC_GEMM_CTA_GROUP")
         eps2 = net(x, torch.full((B,), 500, dtype=torch.long, device=DEV), cond=cond)
-        assert torch.equal(eps2, groups[500])
-    # per-sample independence at this batch: sample 17 alone gives the same bits (no cross-sample op on the path)
+        assert torch.equal(eps2, groups[500]), ("cta_group 1 vs 2", common.rel_l2(eps2, groups[500]))
+    # per-sample independence at this batch (no cross-sample op on the path): sample 17 alone gives the same eps up to
+    # bf16 rounding noise -- not the same bits: the N tile, hence the epilogue variant and the summation order of the
+    # GroupNorm partial sums, is chosen per batch size (ops.pick_bn)
     lab1 = torch.full((1,), 500, dtype=torch.long, device=DEV)
     e1 = net(x[17:18], lab1, cond=cond[17:18])
     e46 = net(x, torch.full((B,), 500, dtype=torch.long, device=DEV), cond=cond)
-    assert torch.equal(e1[0], e46[17]), common.rel_l2(e1[0], e46[17])
+    assert common.rel_l2(e1[0], e46[17]) < 1e-2, common.rel_l2(e1[0], e46[17])  # measured 5.1e-3; each is ~1e-2 from fp32
+    # ... and running the same batch twice gives the same bits (integer statistics, no floating-point atomics)
+    assert torch.equal(e46, net(x, torch.full((B,), 500, dtype=torch.long, device=DEV), cond=cond))
 
 
 @pytest.mark.parametrize("B", [1, 6])
@@ -153,22 +157,25 @@ def test_fpndm20_ddim10_full_model(full):
     assert torch.equal(y1, y2) and torch.equal(y1, y3)
 
 
-def test_ddim_sweep_trajectories_default_init():
-    """BASELINE configs[3]: DDIM 100 and 1000 steps.  At default-like init (the reference zero-initialises Conv_1 /
-    NIN_3) trajectories are not chaotic, so the whole free-running trajectory end point is compared with the fp32
-    oracle -- the r01 sweep only checked finiteness for these two."""
+def test_ddim_100_and_1000_steps_by_decomposition():
+    """BASELINE configs[3]: DDIM with 100 and 1000 steps (101 / 1001 evaluations, one captured graph each).  Free-running
+    DDIM trajectories of an untrained network separate for ANY two implementations, default-like init included
+    (measured: 0.31 rel-L2 after 100 steps against the fp32 oracle, and 0.20 in the fp32-tolerance mode, DESIGN.md
+    section 5), so the long schedules are checked like the short ones: our captured loop against the oracle sampler
+    driving the same evcdiff network (every label of the schedule is visited, sampler arithmetic in fp32 on both sides).
+    The r01 sweep only checked finiteness for these two."""
     from evcdiff import models as M
     cfg, net, sd = build(common.gpu64_config, 4, active=False)
     g = torch.Generator(device=DEV).manual_seed(33)
     x_T = torch.randn(1, 15, 32, 32, device=DEV, generator=g)
     cond = torch.rand(1, 6, 32, 32, device=DEV, generator=g, dtype=torch.float64) * 2 - 1
-    sched = S.schedule(cfg, DEV)
-    model = lambda x, y: O.ncsnpp_forward(sd, cfg, x, y, cond)
+    model = lambda xx, yy: net(xx, yy, cond=cond)
+    sched = (net.betas, net.alphas, net.alphas_prev)
     for steps in (100, 1000):
         y = M.ddim_sampler(x_T.clone(), net, cond=cond, final_only=True, denoise=True, subsample_steps=steps)
         ref = S.ddim_sampler(x_T.clone(), model, sched, subsample_steps=steps)
         err = common.rel_l2(y[0], ref)
-        assert err < XT_TOL, (steps, err)
+        assert err < 2e-3, (steps, err)
 
 
 def test_unet_plain_deeper_full_size():
@@ -191,8 +198,9 @@ def test_unet_plain_deeper_full_size():
 
 
 def test_generate_frame_micro_batches(full):
-    """pipeline.generate_frame with max_batch < B must equal the one-batch result: same x_T / noise per video, so the
-    frames agree bit for bit (sampling is per-video independent)."""
+    """pipeline.generate_frame with max_batch < B against the one-batch result on the same x_T / noise per video:
+    sampling is per-video independent, so the frames agree up to bf16 rounding noise (the tile configuration, and
+    with it the order of the GroupNorm partial sums, depends on the batch size), and both match the oracle."""
     from evcdiff import pipeline
     cfg, net, sd = full
     B = 5
@@ -204,13 +212,15 @@ def test_generate_frame_micro_batches(full):
     one = pipeline.generate_frame(net, frames01, max_batch=8, **kw)
     two = pipeline.generate_frame(net, frames01, max_batch=2, **kw)
     assert one.shape == (B, 5, 3, 128, 128) and float(one.min()) >= 0.0 and float(one.max()) <= 1.0
-    assert torch.equal(one, two)
+    assert common.rel_l2(one, two) < 1e-2, common.rel_l2(one, two)
+    assert torch.equal(two, pipeline.generate_frame(net, frames01, max_batch=2, **kw))  # same micro-batching: same bits
     # and against the oracle's generate_frame restatement (city_sender.py:326-351) on the same draws
     model = lambda x, y: _oracle_eps(sd, cfg, x, y, 2 * frames01 - 1)
     sched = S.schedule(cfg, DEV)
     ref = S.ddpm_sampler(x_T.clone(), model, sched, lambda i: tape[i], subsample_steps=4)
     ref = torch.clamp((ref + 1) / 2, 0, 1).reshape(B, 5, 3, 128, 128)
-    assert common.rel_l2(one, ref) < 2.5e-2, common.rel_l2(one, ref)  # 4 coarse steps: eps-dominated (see smoke())
+    for got in (one, two):
+        assert common.rel_l2(got, ref) < 2.5e-2, common.rel_l2(got, ref)  # 4 coarse steps: eps-dominated (see smoke())
 
 
 def test_ema_after_engine_exists_repacks(full):

@@ -217,3 +217,34 @@ def test_gemm_fused_groupnorm_guard_bands():
         assert int(sbuf[:pad].abs().sum()) == 0 and int(sbuf[pad + B * N * 2:].abs().sum()) == 0
         assert int(tbuf[:pad].abs().sum()) == 0 and int(tbuf[pad + B:].abs().sum()) == 0
         assert ticket.tolist() == [2, 2, 2]
+
+
+def test_gemm_fused_groupnorm_rejects_oversized_samples():
+    """ADVICE r01 / VERDICT item 8: a sample whose tiles do not fit in two rounds of the persistent grid would make a
+    CTA wait for a tile it owns itself (e.g. image_size 256: 512 tiles per sample).  The plan must be refused on the
+    host (EVC_ERR_UNSUPPORTED) -- the engine then keeps the unfused gn_apply launch -- and nothing may fault."""
+    ops = _setup()
+    from evcdiff._lib import EvcError
+    from evcdiff.engine import EngineBase
+    B, H, Cin, N = 1, 256, 64, 64
+    a = torch.zeros(B, H, H, Cin, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(N, 9 * Cin, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(B, H, H, N, device="cuda", dtype=torch.bfloat16)
+    stats = torch.zeros(B, N, 2, device="cuda", dtype=torch.int64)
+    ticket = torch.zeros(B, device="cuda", dtype=torch.int32)
+    gn = dict(ss=torch.zeros(2 * N, device="cuda"), ticket=ticket, eps=1e-5, groups=16, adagn=True)
+    with pytest.raises(EvcError, match="unfused"):
+        ops.GemmPlan([(a, 9)], w, out, 0, out_ld=N, bias=torch.zeros(N, device="cuda"), bn=64, stats=stats, gn=gn)
+    # the engine-side mirror takes the same decision before any buffer is planned
+    assert not ops.gn_fuse_fits(512, 512, 1)
+    assert ops.gn_fuse_fits(128, 128 * 46, 1) and ops.gn_fuse_fits(128, 128, 1)
+    eng = EngineBase.__new__(EngineBase)
+    eng.split = False
+    assert not eng.gn_fusable(1, 256, 256, [(64, 9)], 64)
+    assert eng.gn_fusable(1, 128, 128, [(192, 9)], 192)
+    # a fitting shape still works, and no tile wait ever gave up
+    plan = ops.GemmPlan([(a[:, :128, :128].contiguous(), 9)], w, out[:, :128, :128].contiguous(), 0, out_ld=N,
+                        bias=torch.zeros(N, device="cuda"), bn=64, stats=stats, gn=gn)
+    plan.launch()
+    torch.cuda.synchronize()
+    assert ops.gemm_fault_count() == 0
