@@ -103,6 +103,14 @@ struct alignas(64) GemmParams {
   int sample_rows;    // TW*TH
   int stride;         // convolution stride (1 or 2): input coordinate = stride * output coordinate + tap offset
   int m_tiles;        // tiles_x * tiles_y * tiles_b
+  // split-K (few M tiles: small batches, 8x8 / 16x16 levels): a work unit is (tile, K slice); every unit writes its fp32
+  // partial tile to `sk_ws`, the unit that arrives last on the tile's ticket adds the slices in the fixed order
+  // 0..split_k-1 (deterministic whatever the arrival order) and runs the normal epilogue on the sum
+  int split_k;
+  float* sk_ws;            // [split_k][m_tiles_padded * 128][sk_ld] fp32
+  int* sk_ticket;          // [total_tiles * CG], zero before the first launch; reset by the last arriver
+  long long sk_plane;      // elements per K-slice plane
+  int sk_ld;               // tiles_n * BN
 };
 
 // Work unit `tile` of a CTA (CG = 1) or CTA pair (CG = 2): N tile tn = tile % tiles_n, M tile(s) CG*(tile/tiles_n)+rank.
@@ -242,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
 
   const int m_pairs = (p.m_tiles + CG - 1) / CG;
   const int total_tiles = m_pairs * p.tiles_n;
+  const int total_units = total_tiles * p.split_k;  // split_k == 1: a unit is a tile
   pdl_wait();     // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
   pdl_trigger();
 
@@ -252,11 +261,15 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     uint32_t phase = 0;
     PROF_DECL(long long w_empty = 0;)
     PROF_T0(t_prod);
-    for (int tile = unit; tile < total_tiles; tile += num_units) {
+    for (int u = unit; u < total_units; u += num_units) {
+      const int tile = u / p.split_k;
+      const int ks = u - tile * p.split_k;
+      const int kb_lo = (ks * p.total_kb) / p.split_k, kb_hi = ((ks + 1) * p.total_kb) / p.split_k;
       int x0, y0, b0, n0;
       decode_tile<CG>(p, tile, rank, x0, y0, b0, n0);
       const int zb = p.b_batched ? b0 : 0;
       const int nb = n0 + rank * (p.BN / CG);  // this CTA's half of the B tile
+      int kb = 0;
       for (int s = 0; s < p.n_seg; ++s) {
         const int taps = p.seg_taps[s];
         const CUtensorMap* am = &p.a_map[p.seg_a[s]];
@@ -265,7 +278,8 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           const int ktap = p.seg_koff[s] + t * p.seg_c[s];
           const int dy = (taps == 9) ? (t / 3 - 1) : 0;
           const int dx = (taps == 9) ? (t % 3 - 1) : 0;
-          for (int c = 0; c < p.seg_kb[s]; ++c) {
+          for (int c = 0; c < p.seg_kb[s]; ++c, ++kb) {
+            if (kb < kb_lo || kb >= kb_hi) continue;  // another unit's K slice
             PROF_T0(t_e);
             mbar_wait(empty_bar(stage), phase ^ 1u);
             PROF_ADD(w_empty, t_e);
@@ -307,7 +321,9 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     int it = 0;
     PROF_DECL(long long w_full = 0; long long w_tempty = 0;)
     PROF_T0(t_mma);
-    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
+    for (int u = unit; u < total_units; u += num_units, ++it) {
+      const int ks = u % p.split_k;
+      const int kb_lo = (ks * p.total_kb) / p.split_k, kb_hi = ((ks + 1) * p.total_kb) / p.split_k;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       PROF_T0(t_te);
@@ -315,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       PROF_ADD(w_tempty, t_te);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * kAccStride;
-      for (int kb = 0; kb < p.total_kb; ++kb) {
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
         PROF_T0(t_f);
         mbar_wait(full_bar(stage), phase);
         PROF_ADD(w_full, t_f);
@@ -332,15 +348,16 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
 #else
             const uint32_t td = tmem_d;
 #endif
-            if (CG == 2) umma_bf16_2sm(td, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(td, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t accum = (kb != kb_lo || k != 0) ? 1u : 0u;
+            if (CG == 2) umma_bf16_2sm(td, da + 2u * k, db + 2u * k, idesc, accum);
+            else umma_bf16(td, da + 2u * k, db + 2u * k, idesc, accum);
           }
           if (CG == 2) {
             umma_commit_2sm(empty_bar(stage), 3);  // frees this stage in both CTAs
-            if (kb == p.total_kb - 1) umma_commit_2sm(tfull_bar(acc), 3);
+            if (kb == kb_hi - 1) umma_commit_2sm(tfull_bar(acc), 3);
           } else {
             umma_commit(empty_bar(stage));
-            if (kb == p.total_kb - 1) umma_commit(tfull_bar(acc));
+            if (kb == kb_hi - 1) umma_commit(tfull_bar(acc));
           }
         }
         __syncwarp();
@@ -469,7 +486,10 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     int it = 0;
     PROF_DECL(long long w_tfull = 0; long long w_pre = 0; long long w_ld = 0; long long w_rest = 0;)
     PROF_T0(t_epi);
-    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
+    int rit = 0;  // residual tiles fetched by TMA so far (phase of resid_bar)
+    volatile int* sk_flag = reinterpret_cast<volatile int*>(tail + 192);  // free bytes of the barrier block
+    for (int u = unit; u < total_units; u += num_units, ++it) {
+      const int tile = u / p.split_k;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       int x0, y0, b0, n0;
@@ -480,6 +500,47 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       const long long pix = (long long)b * p.H * p.W + pin;
       const bool full_n = (n0 + p.BN <= p.N);
       const bool resid_fast = (p.resid != nullptr) && p.resid_smem && full_n;
+      const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      bool from_ws = false;
+      const float* ws_row = nullptr;
+      if (p.split_k > 1) {
+        // ---- split-K, phase A (every unit): accumulator -> this K slice's fp32 plane, one ticket per (tile, CTA rank)
+        const int ks = u - tile * p.split_k;
+        const long long tm = (long long)(tile / p.tiles_n) * CG + rank;
+        float* wrow = p.sk_ws + (long long)ks * p.sk_plane + (tm * 128 + row) * p.sk_ld + n0;
+        ws_row = p.sk_ws + (tm * 128 + row) * p.sk_ld + n0;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {  // BN % 32 == 0 (checked by the host)
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            __stcg(reinterpret_cast<float4*>(wrow + c0 + j),
+                   make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                               __uint_as_float(v[j + 3])));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+          else mbar_arrive(tempty_bar(acc));
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (e == 0) {
+          int* tk = p.sk_ticket + (long long)tile * CG + rank;
+          const int seen = atomicAdd(tk, 1);
+          const int last = (seen == p.split_k - 1) ? 1 : 0;
+          if (last) *tk = 0;  // every slice has arrived: ready for the next launch
+          *sk_flag = last;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (*sk_flag == 0) continue;  // another unit adds the slices up
+        __threadfence();
+        from_ws = true;
+      }
       // (1) prefetch
       PROF_T0(t_pre);
       asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone is done with the previous tile's sbias
@@ -508,12 +569,16 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       PROF_ADD(w_pre, t_pre);
       // (2) accumulator ready
       PROF_T0(t_tf);
-      mbar_wait(tfull_bar(acc), acc_phase);
+      if (!from_ws) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+      }
       PROF_ADD(w_tfull, t_tf);
-      tc_fence_after();
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      if (p.resid_tma) mbar_wait(resid_bar, static_cast<uint32_t>(it) & 1u);
-      const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      if (p.resid_tma) {
+        mbar_wait(resid_bar, static_cast<uint32_t>(rit) & 1u);
+        ++rit;
+      }
       if (!SPLIT && p.gn_fuse) {
         // ---- fused GroupNorm apply.  Pass 1 (this tile): bf16(acc + bias) -> this tile's slot in shared memory
         // (TMA-store layout: [chunk][row quarter][32 rows x 64 B, 64 B swizzle]) + column sums -> statistics + one
@@ -599,19 +664,39 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         gn_pix = ((long long)b0 * p.H + y0) * p.W + x0;
         continue;
       }
-      bool released = false;
+      bool released = from_ws;  // split-K: the accumulator was handed back in phase A
       for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
         const int ncols = min(32, p.BN - c0);
         uint32_t v[32];
         PROF_T0(t_ld);
-        if (ncols == 32)
-          tmem_ld_32x32(taddr + c0, v);
-        else
-          tmem_ld_32x16(taddr + c0, v);
-        tmem_ld_wait();
+        if (from_ws) {
+          // split-K, phase B (last arriver): slices added in the fixed order 0, 1, ..., split_k-1
+          float sacc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sacc[j] = 0.f;
+          for (int ks = 0; ks < p.split_k; ++ks) {
+            const float* src = ws_row + (long long)ks * p.sk_plane + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + j));
+              sacc[j] += t4.x;
+              sacc[j + 1] += t4.y;
+              sacc[j + 2] += t4.z;
+              sacc[j + 3] += t4.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(sacc[j]);
+        } else {
+          if (ncols == 32)
+            tmem_ld_32x32(taddr + c0, v);
+          else
+            tmem_ld_32x16(taddr + c0, v);
+          tmem_ld_wait();
+        }
         PROF_ADD(w_ld, t_ld);
         PROF_T0(t_rest);
-        if (c0 + 64 >= p.BN) {
+        if (!from_ws && c0 + 64 >= p.BN) {
           released = true;
           // last TMEM read of this tile is complete: hand the accumulator stage back to the MMA warp
           tc_fence_before();
@@ -970,6 +1055,8 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
       if (pair_tiles >= 2LL * (evc_num_sms() / 2)) cg = 2;
     }
   }
+  const int split_k = d->split_k > 1 ? d->split_k : 1;
+  if (split_k > 1 && d->cta_group == 0) cg = 1;  // few tiles: nothing to pair
   pl->cg = cg;
 
   const int cs = d->stride <= 1 ? 1 : d->stride;
@@ -1141,6 +1228,24 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     // two staging buffers per epilogue warp unless that would leave fewer than four pipeline stages
     p.tma_out = (tma_env >= 2 && (227 * 1024 - 1024 - layout(2)) / stage_bytes >= 4) ? 2 : 1;
   }
+  p.split_k = 1;
+  if (split_k > 1) {
+    const long long rows = (long long)((p.m_tiles + cg - 1) / cg) * cg * 128;
+    const long long ld = (long long)p.tiles_n * d->bn;
+    const long long need = (long long)split_k * rows * ld * 4;
+    if ((d->bn % 32) != 0 || split || d->gn_ss != nullptr || d->sk_ws == nullptr || d->sk_ticket == nullptr ||
+        split_k > total_kb || d->sk_ws_bytes < need || (reinterpret_cast<uintptr_t>(d->sk_ws) & 15)) {
+      delete pl;
+      return evc_set_error(EVC_ERR_INVALID,
+                           "split_k needs bn % 32 == 0, no gn_ss / split-precision planes, split_k <= K blocks, and a "
+                           "16-byte aligned sk_ws of split_k * roundup(m_tiles) * 128 * tiles_n * bn floats + sk_ticket");
+    }
+    p.split_k = split_k;
+    p.sk_ws = reinterpret_cast<float*>(d->sk_ws);
+    p.sk_ticket = d->sk_ticket;
+    p.sk_plane = rows * ld;
+    p.sk_ld = (int)ld;
+  }
   p.gn_fuse = 0;
   if (d->gn_ss != nullptr) {
     const bool ok = p.tma_out != 0 && d->stats != nullptr && d->gn_ticket != nullptr && d->bias != nullptr &&
@@ -1198,7 +1303,7 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   p.num_stages = stages;
   pl->smem_bytes = stages * stage_bytes + 1024 + tail_bytes;
 
-  const long long units = (long long)((p.m_tiles + cg - 1) / cg) * p.tiles_n;  // tiles (cg 1) or tile pairs (cg 2)
+  const long long units = (long long)((p.m_tiles + cg - 1) / cg) * p.tiles_n * p.split_k;  // (tile | tile pair) x K slice
   int sms = evc_num_sms();
   int cap = (d->max_ctas > 0 ? d->max_ctas : sms) / cg;
   if (cap < 1) cap = 1;

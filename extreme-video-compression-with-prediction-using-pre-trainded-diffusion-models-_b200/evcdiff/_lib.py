@@ -31,7 +31,8 @@ class GemmDesc(C.Structure):
                 ("alpha", C.c_float), ("max_ctas", C.c_int32), ("stats", C.c_void_p), ("stride", C.c_int32), ("cta_group", C.c_int32),
                 ("a_lo", Tensor4 * 3), ("w_lo", C.c_void_p), ("out_lo", C.c_void_p), ("resid_lo", C.c_void_p),
                 ("gn_ss", C.c_void_p), ("gn_ticket", C.c_void_p), ("gn_eps", C.c_float), ("gn_groups", C.c_int32),
-                ("gn_adagn", C.c_int32)]
+                ("gn_adagn", C.c_int32), ("split_k", C.c_int32), ("sk_ws", C.c_void_p), ("sk_ws_bytes", C.c_int64),
+                ("sk_ticket", C.c_void_p)]
 
 
 class AttnDesc(C.Structure):

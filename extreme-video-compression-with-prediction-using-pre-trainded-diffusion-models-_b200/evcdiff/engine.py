@@ -129,6 +129,8 @@ class EngineBase:
         self.fixed_groups = None  # models/unet.py: always 32 groups; NCSN++: min(C//4, 32)
         self.fused_attention = os.environ.get("EVC_FUSED_ATTENTION", "1") != "0"
         self.ws_bytes = 256
+        # split-K partial tiles (fp32) of the launches with few M tiles; one buffer, the launches are stream-ordered
+        self.sk_ws = None if self.split else torch.empty(ops.SPLIT_K_WS_BYTES, dtype=torch.uint8, device=self.device)
 
     # ----------------------------------------------------------------- recording helpers
     def _op(self, fn, kind="other", meta=None):
@@ -172,6 +174,8 @@ class EngineBase:
             return False
         kblocks = sum(taps * (-(-c // 64)) for c, taps in cin_segs)
         mt = ops.m_tiles(B, H, W, False)
+        if ops.pick_tile(cout, mt, kblocks)[1] > 1:
+            return False  # few tiles (small batch / low resolution): split-K + a separate gn_apply launch is faster
         bn = ops.pick_bn(cout, mt, kblocks)
         if bn % 32 != 0 or bn > 192:  # two bn x 256 B tile slots + >= 3 pipeline stages must fit in 227 KB
             return False
@@ -249,7 +253,8 @@ class EngineBase:
             stats_t = ("deferred", stats_of)
         plan_args = dict(out_bs=out_bs, bias=bias, resid=resid.t if isinstance(resid, Act) else resid,
                          resid_ld=(resid.C if isinstance(resid, Act) else 0), alpha=alpha, stride=stride,
-                         segs_lo=segs_lo, w_lo=w_lo, out_lo=out_lo, resid_lo=resid_lo)
+                         segs_lo=segs_lo, w_lo=w_lo, out_lo=out_lo, resid_lo=resid_lo,
+                         split_k="auto", sk_ws=self.sk_ws)
         a0 = seg_t[0][0]
         shp = tuple(a0.shape)
         M = shp[0] * (shp[1] // stride) * (shp[2] // stride)

@@ -29,7 +29,7 @@ class GemmPlan:
 
     def __init__(self, segs, w, out, out_mode, out_ld, out_bs=0, bias=None, resid=None, resid_ld=0, alpha=1.0,
                  bn=None, max_ctas=0, stats=None, stride=1, cta_group=None, segs_lo=None, w_lo=None, out_lo=None,
-                 resid_lo=None, gn=None):
+                 resid_lo=None, gn=None, split_k=1, sk_ws=None):
         lib = load()
         _require_cuda(w, out, bias, resid, *[s[0] for s in segs])
         d = GemmDesc()
@@ -56,9 +56,15 @@ class GemmPlan:
         d.w = w.data_ptr()
         d.B, d.H, d.W = B, H, W_
         n = d.w_rows
+        kblocks = sum(taps * (-(-a.shape[3] // 64)) for a, taps in segs)
+        can_split = (split_k == "auto" and w.dim() == 2 and gn is None and w_lo is None and sk_ws is not None)
         if bn is None:
-            kblocks = sum(taps * (-(-a.shape[3] // 64)) for a, taps in segs)
-            bn = pick_bn(n, m_tiles(B, H, W_, w.dim() == 3), kblocks)
+            bn, auto_s = pick_tile(n, m_tiles(B, H, W_, False), kblocks, allow_split=can_split) if w.dim() == 2 else \
+                (pick_bn(n, m_tiles(B, H, W_, True), kblocks), 1)
+        else:
+            auto_s = 1
+        if split_k == "auto":
+            split_k = auto_s if can_split else 1
         d.bn = bn
         d.out = out.data_ptr()
         d.out_mode = out_mode
@@ -100,7 +106,21 @@ class GemmPlan:
             d.gn_eps = float(gn["eps"])
             d.gn_groups = int(gn["groups"])
             d.gn_adagn = int(bool(gn["adagn"]))
-        self._keep = (segs, w, out, bias, resid, stats, segs_lo, w_lo, out_lo, resid_lo, gn)
+        self.split_k = 1
+        sk_ticket = None
+        if split_k and split_k > 1:
+            # split-K: K slices of a tile on different CTAs, slices added in a fixed order by the last arriver
+            mt2 = (m_tiles(B, H, W_, w.dim() == 3) + 1) // 2 * 2
+            tiles_n = -(-n // bn)
+            need = split_k * mt2 * 128 * tiles_n * bn * 4
+            assert sk_ws is not None and sk_ws.numel() * sk_ws.element_size() >= need, "split-K workspace too small"
+            sk_ticket = torch.zeros(mt2 * tiles_n, dtype=torch.int32, device=out.device)
+            d.split_k = int(split_k)
+            d.sk_ws = sk_ws.data_ptr()
+            d.sk_ws_bytes = sk_ws.numel() * sk_ws.element_size()
+            d.sk_ticket = sk_ticket.data_ptr()
+            self.split_k = int(split_k)
+        self._keep = (segs, w, out, bias, resid, stats, segs_lo, w_lo, out_lo, resid_lo, gn, sk_ws, sk_ticket)
         self._lib = lib
         h = C.c_void_p()
         check(lib.evc_gemm_plan_create(C.byref(d), C.byref(h)), "evc_gemm_plan_create")
@@ -190,6 +210,41 @@ def pick_bn(n, mt=None, kblocks=None, sms=148):
         if best_cost is None or cost < best_cost * 0.97:  # prefer wider tiles unless clearly slower
             best, best_cost = bn, cost
     return best
+
+
+SPLIT_K_WS_BYTES = 48 << 20  # fp32 partial tiles of one split-K launch (pick_tile keeps its choices below this)
+TMA_CYCLES_PER_ROW = 2.4     # measured: one SM's TMA unit delivers a 128-byte box row every ~2.4 cycles (profiles/r02_notes.md)
+
+
+def pick_tile(n, mt, kblocks, sms=None, allow_split=True):
+    """(N tile, K slices) of a launch.  Large problems: the widest N tile (fewest operand re-reads per FLOP), one slice.
+    Launches with few 128-row M tiles (small batches, the 8x8 / 16x16 levels) are bound by how fast ONE SM streams its
+    operands -- 128 A rows + bn B rows per 64-wide K block through the TMA unit -- so instead of shrinking the N tile
+    until every SM has a tile (which re-reads A once per N tile), the K loop of a wide tile is cut into slices that run
+    on otherwise idle SMs (split-K, slices summed in a fixed order)."""
+    sms = sms or num_sms()
+    if not allow_split or os.environ.get("EVC_GEMM_SPLIT_K", "1") == "0":
+        return pick_bn(n, mt, kblocks, sms), 1
+    cands = [bn for bn in (256, 192, 128, 96, 64, 48, 32, 16) if n % bn == 0]
+    if not cands:
+        return pick_bn(n, mt, kblocks, sms), 1
+    best = None
+    for bn in cands:
+        tiles = mt * (n // bn)
+        cg = 2 if ((mt + 1) // 2) * (n // bn) >= 2 * (sms // 2) and bn % 16 == 0 else 1
+        per_kb = max(2 * bn, TMA_CYCLES_PER_ROW * (128 + bn / cg))
+        for S in (1, 2, 3, 4, 6, 8, 12, 16):
+            if S > 1 and (bn % 32 != 0 or kblocks // S < 4 or tiles * S > sms or
+                          S * ((mt + 1) // 2 * 2) * 128 * n * 4 > SPLIT_K_WS_BYTES):
+                continue
+            waves = -(-(tiles * S) // sms)
+            cost = waves * (-(-kblocks // S) * per_kb + 1500 + 12 * bn)
+            if S > 1:
+                cost += 8 * S * bn + 2500  # last arriver re-reads the S partial tiles; ticket round trip
+            key = (cost * (1.0 if best is None else 1.0), -bn)
+            if best is None or cost < best[0] * 0.97:  # prefer wider tiles / fewer slices unless clearly slower
+                best = (cost, bn, S)
+    return best[1], best[2]
 
 
 def gn_fuse_fits(sample_m_tiles, m_tiles_total, tiles_n, sms=None):

@@ -127,6 +127,18 @@ typedef struct evc_gemm_desc {
   float gn_eps;
   int32_t gn_groups;
   int32_t gn_adagn;
+  /* Split-K for launches with few M tiles (small batches; the 8x8 / 16x16 levels): split_k > 1 cuts the K loop of
+   * every tile into split_k slices handled by different CTAs; each writes its fp32 partial tile to sk_ws, and the
+   * CTA that arrives last on the tile's ticket adds the slices in the fixed order 0..split_k-1 (bit-reproducible
+   * whatever the arrival order) and runs the normal epilogue (bias, residual, alpha, store, fused statistics).
+   * 0 / 1 = off.  Needs bn % 32 == 0, no gn_ss, no split-precision planes.
+   * sk_ws: split_k * roundup2(m_tiles) * 128 * (ceil(N / bn) * bn) floats (sk_ws_bytes is checked); may be shared
+   * by plans that run one after the other on a stream.  sk_ticket: ceil(N / bn) * roundup2(m_tiles) int32, zero
+   * before the first launch (the kernel leaves them zero), NOT shared between plans in flight. */
+  int32_t split_k;
+  void* sk_ws;
+  int64_t sk_ws_bytes;
+  int32_t* sk_ticket;
 } evc_gemm_desc;
 
 typedef struct evc_gemm_plan evc_gemm_plan;

@@ -248,3 +248,66 @@ def test_gemm_fused_groupnorm_rejects_oversized_samples():
     plan.launch()
     torch.cuda.synchronize()
     assert ops.gemm_fault_count() == 0
+
+
+SPLITK_CASES = [
+    # name, B, H, W, [(C, taps)], N, out_mode, resid, alpha, bn, split_k, cta_group
+    ("sk_w8_n768_s4", 6, 8, 8, [(768, 9)], 768, 0, True, 0.70710678, 96, 6, 1),
+    ("sk_w8_skip_s3", 5, 8, 8, [(576, 9), (768, 1), (576, 1)], 768, 0, False, 0.70710678, 256, 3, 1),
+    ("sk_w16_n576_s4", 3, 16, 16, [(384, 9)], 576, 0, False, 1.0, 192, 4, 1),
+    ("sk_w16_pair_s2", 4, 16, 16, [(192, 9)], 384, 0, True, 1.0, 128, 2, 2),
+    ("sk_w32_f32rows_s5", 1, 32, 32, [(192, 9)], 384, 1, False, 1.0, 64, 5, 1),
+    ("sk_w8_f32T_s7", 1, 8, 8, [(576, 9)], 64, 3, False, 1.0, 32, 7, 1),
+    ("sk_uneven_kb_s4", 2, 8, 8, [(192, 9), (64, 1)], 256, 0, False, 1.0, 128, 4, 1),  # 28 K blocks over 4 slices
+]
+
+
+@pytest.mark.parametrize("case", SPLITK_CASES, ids=[c[0] for c in SPLITK_CASES])
+def test_split_k_gemm(case):
+    """Split-K (evc_gemm_desc.split_k): K slices of a tile on different CTAs, fp32 partial tiles in a workspace, the last
+    arriver adds them in the fixed order 0..S-1 and runs the normal epilogue (bias, residual, alpha, TMA / per-thread
+    stores, fused GroupNorm statistics).  Against torch fp32, against the unsplit launch (same values up to the fp32
+    summation order: identical after bf16 rounding except for rare last-bit flips), and bit-identical run to run."""
+    ops = _setup()
+    name, B, H, W, segspec, N, out_mode, use_resid, alpha, bn, S, cg = case
+    g = torch.Generator(device="cuda").manual_seed(hash(name) % 2**31)
+    segs = [(torch.randn(B, H, W, Cc, device="cuda", generator=g).bfloat16(), taps) for Cc, taps in segspec]
+    K = sum(Cc * taps for Cc, taps in segspec)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(B, H, W, N, device="cuda", generator=g).bfloat16() if use_resid else None
+    ws = torch.empty(ops.SPLIT_K_WS_BYTES, dtype=torch.uint8, device="cuda")
+    dt = torch.bfloat16 if out_mode == 0 else torch.float32
+    shape = (B, H, W, N) if out_mode in (0, 1) else (B, N, H, W)
+    ld, bs = (N, 0) if out_mode in (0, 1) else (H * W, N * H * W)
+    want_stats = out_mode == 0 and (H * W) % 32 == 0
+    res = {}
+    for split in (1, S):
+        outs = []
+        for rep in range(3):
+            out = torch.full(shape, float("nan"), device="cuda", dtype=dt)
+            st = torch.zeros(B, N, 2, device="cuda", dtype=torch.int64) if want_stats else None
+            plan = ops.GemmPlan(segs, w, out, out_mode, out_ld=ld, out_bs=bs, bias=bias, resid=resid, resid_ld=N, alpha=alpha,
+                                bn=bn, stats=st, cta_group=cg, split_k=split, sk_ws=ws)
+            assert plan.split_k == split
+            plan.launch()
+            plan.launch()  # tickets are left at zero by the last arriver: relaunch without any reset
+            torch.cuda.synchronize()
+            outs.append((out, st))
+        assert torch.isfinite(outs[0][0].float()).all(), f"{name}: unwritten outputs (split_k={split})"
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], outs[2][0]), f"{name}: not reproducible"
+        res[split] = outs[0]
+    ref = ref_conv(segs, w, bias, resid, alpha)
+    got = res[S][0].float()
+    got = got.permute(0, 3, 1, 2) if out_mode in (0, 1) else got
+    assert rel_l2(got, ref) < (4e-3 if out_mode == 0 else 2e-5), f"{name}: rel-L2 {rel_l2(got, ref):.3e}"
+    base = res[1][0].float()
+    base = base.permute(0, 3, 1, 2) if out_mode in (0, 1) else base
+    assert rel_l2(got, base) < (2e-3 if out_mode == 0 else 2e-6), f"{name}: split vs unsplit {rel_l2(got, base):.3e}"
+    if want_stats:
+        # statistics of the stored bf16 values: each launch's statistics match its own output (two launches accumulated)
+        o = res[S][0].float()
+        s_ref = torch.stack([o.sum(dim=(1, 2)), (o * o).sum(dim=(1, 2))], -1) * 2
+        s_got = res[S][1].double() / 2 ** 20
+        assert rel_l2(s_got, s_ref) < 1e-4, f"{name}: fused statistics {rel_l2(s_got, s_ref):.3e}"
+    assert ops.gemm_fault_count() == 0
