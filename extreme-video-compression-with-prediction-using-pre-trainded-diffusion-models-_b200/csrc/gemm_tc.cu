@@ -25,8 +25,17 @@ namespace evc {
 
 constexpr int kMaxStages = 8;
 constexpr int kABytes = 128 * 64 * 2;  // one A stage: 128 rows x 64 bf16
-constexpr int kEpiThreads = 256;  // 8 epilogue warps: two per TMEM lane quarter, alternating 32-column chunks
+#ifndef EVC_EPI_WARPS
+#define EVC_EPI_WARPS 8
+#endif
+// epilogue warps: kEpiGroups per TMEM lane quarter, each taking every kEpiGroups-th 32-column chunk of the tile.  The
+// epilogue is latency-bound (TMEM loads, shared-memory round trips, shuffles), so it wants warps, not registers
+constexpr int kEpiThreads = 32 * EVC_EPI_WARPS;
+constexpr int kEpiGroups = kEpiThreads / 128;
+constexpr int kChunkStride = 32 * kEpiGroups;  // columns between two chunks of one warp
 constexpr int kThreads = 128 + kEpiThreads;
+static_assert(EVC_EPI_WARPS % 4 == 0 && EVC_EPI_WARPS >= 4 && EVC_EPI_WARPS <= 16, "whole groups of four epilogue warps");
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 
@@ -62,6 +71,7 @@ struct alignas(64) GemmParams {
   CUtensorMap resid_map; // residual as a 2-D tensor (N, B*H*W), 64 x 128 boxes, 128 B swizzle
   int resid_tma;         // 1: the tile's residual rows are fetched by TMA (needs tma_out), 0: cp.async per thread
   int off_resid, off_stat, off_stage;  // byte offsets of the epilogue scratch areas behind the barrier block
+  int off_coef;          // fused GroupNorm apply: [2][BN] (a, b) coefficient pairs written by the coordinator warp
   // fused GroupNorm apply: the epilogue keeps the accumulator in TMEM until every tile of the sample has contributed
   // its statistics (per-sample ticket), then writes SiLU(GN(acc + bias) * gamma' + beta') instead of the raw value
   int gn_fuse;
@@ -71,6 +81,7 @@ struct alignas(64) GemmParams {
   int gn_cpg, gn_adagn, tiles_per_sample;
 #ifdef EVC_GEMM_PROF
   int exp_alt;           // timing experiment (wrong results): alternate the accumulator between consecutive MMAs
+  int exp_skip;          // timing experiment (wrong results): skip operand loads, see the producer loop
 #endif
   int n_seg;             // number of virtual segments
   int seg_a[kMaxVSeg];   // a_map index
@@ -107,7 +118,7 @@ struct alignas(64) GemmParams {
   // partial tile to `sk_ws`, the unit that arrives last on the tile's ticket adds the slices in the fixed order
   // 0..split_k-1 (deterministic whatever the arrival order) and runs the normal epilogue on the sum
   int split_k;
-  float* sk_ws;            // [split_k][m_tiles_padded * 128][sk_ld] fp32
+  float* sk_ws;            // [split_k][m_tiles_padded][sk_ld columns][128 rows] fp32
   int* sk_ticket;          // [total_tiles * CG], zero before the first launch; reset by the last arriver
   long long sk_plane;      // elements per K-slice plane
   int sk_ld;               // tiles_n * BN
@@ -218,6 +229,10 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
   const uint32_t resid_bar = bar_base + 8u * (2 * kMaxStages + 5);  // TMA-fetched residual tile landed
+  // fused GroupNorm apply (slot s = tile parity): statistics of the tile issued | coefficients ready | coefficients read
+  auto gn_stat_bar = [&](int s) { return bar_base + 200u + 8u * s; };
+  auto gn_coef_bar = [&](int s) { return bar_base + 216u + 8u * s; };
+  auto gn_free_bar = [&](int s) { return bar_base + 232u + 8u * s; };
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_seg; ++s) tma_prefetch_desc(&p.a_map[p.seg_a[s]]);
@@ -234,6 +249,11 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       mbar_init(tempty_bar(s), CG * (kEpiThreads / 32));  // one arrival per epilogue warp of every CTA
     }
     mbar_init(resid_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(gn_stat_bar(s), kEpiThreads / 32);
+      mbar_init(gn_coef_bar(s), 1);
+      mbar_init(gn_free_bar(s), kEpiThreads / 32);
+    }
     fence_mbar_init();
   }
   if (CG == 2) cluster_sync_all();  // peer barriers initialised before anyone signals them; both CTAs alive
@@ -284,17 +304,27 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
             mbar_wait(empty_bar(stage), phase ^ 1u);
             PROF_ADD(w_empty, t_e);
             const uint32_t sa = base + stage * stage_bytes;
+#ifdef EVC_GEMM_PROF
+            // timing experiments (wrong results): 1 = A only for the first tap of each row of taps, 4 = A only for tap 0,
+            // 2 = B only for the first K block of a unit -- how much of the K-block time is operand delivery?
+            const bool ld_a = !(((p.exp_skip & 1) && (t % 3) != 0) || ((p.exp_skip & 4) && t != 0));
+            const bool ld_b = !((p.exp_skip & 2) && kb != kb_lo);
+            const uint32_t txb = (ld_a ? static_cast<uint32_t>(p.rows_valid) * 128u : 0u) + (ld_b ? b_bytes : 0u);
+#else
+            const bool ld_a = true, ld_b = true;
+            const uint32_t txb = p.tx_bytes;
+#endif
             if (elect_one()) {
               if (CG == 2) {
                 // both CTAs' bytes land on the leader's barrier; the peer contributes a plain (remote) arrival
-                if (rank == 0) mbar_expect_tx(full_bar(stage), p.tx_bytes * 2u);
+                if (rank == 0) mbar_expect_tx(full_bar(stage), txb * 2u);
                 else mbar_arrive_cluster(full_bar(stage), 0);
-                tma_load_4d_2sm(am, sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
-                tma_load_3d_2sm(bm, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
+                if (ld_a) tma_load_4d_2sm(am, sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
+                if (ld_b) tma_load_3d_2sm(bm, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
               } else {
-                mbar_expect_tx(full_bar(stage), p.tx_bytes);
-                tma_load_4d(am, sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
-                tma_load_3d(bm, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
+                mbar_expect_tx(full_bar(stage), txb);
+                if (ld_a) tma_load_4d(am, sa, full_bar(stage), c * 64, x0 * p.stride + dx, y0 * p.stride + dy, b0);
+                if (ld_b) tma_load_3d(bm, sa + kABytes, full_bar(stage), ktap + c * 64, nb, zb);
               }
             }
             __syncwarp();
@@ -340,6 +370,9 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         const uint64_t da = umma_desc_sw128(sa);
         const uint64_t db = umma_desc_sw128(sa + kABytes);
         if (elect_one()) {
+#ifdef EVC_GEMM_PROF
+          if (!(p.exp_skip & 8))  // timing experiment: no MMAs at all (commits only): pure operand-delivery rate
+#endif
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
@@ -375,6 +408,119 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       PROF_OUT(2, w_tempty);
       PROF_OUT(7, 1);
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ fused GroupNorm apply: coordinator.
+    // Everything that waits for global memory is kept off the epilogue warps: for each tile of this CTA, once the
+    // epilogue has issued the tile's statistics (gn_stat_bar), publish one ticket for the sample, wait until every tile
+    // of the sample has published its own, fetch the sample's channel sums once (one L2 round trip), turn them into
+    // per-column (a, b) with y = a * x + b, and hand them to the epilogue's pass 2 (gn_coef_bar).
+    if (!SPLIT && p.gn_fuse) {
+      uint8_t* tail3 = smem_raw + (bar_base - smem_u32(smem_raw));
+      float2* scoef_all = reinterpret_cast<float2*>(tail3 + p.off_coef);
+      int it = 0;
+      int pub = 0;  // tickets of this CTA's tiles [0, pub) are published
+      // the statistics atomics of the epilogue threads happen before their arrivals on gn_stat_bar, which this warp has
+      // observed: the fence makes them visible device-wide before the ticket is
+      auto publish = [&](int b) {
+        if (lane == 0) {
+          __threadfence();
+          asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p.gn_ticket + b), "r"(1) : "memory");
+        }
+      };
+      for (int u = unit; u < total_units; u += num_units, ++it) {
+        int x0, y0, b0, n0;
+        decode_tile<CG>(p, u, rank, x0, y0, b0, n0);
+        if (b0 >= p.B) continue;  // the peer CTA of an odd last pair has no tile
+        const int slot = it & 1;
+        const uint32_t par = (it >> 1) & 1u;
+        if (pub <= it) {
+          mbar_wait(gn_stat_bar(slot), par);
+          publish(b0);
+          pub = it + 1;
+        }
+        // the next tile may belong to the same sample: its ticket must go out while this one is being waited for
+        int b0n = p.B;
+        if (u + num_units < total_units) {
+          int xn, yn, nn;
+          decode_tile<CG>(p, u + num_units, rank, xn, yn, b0n, nn);
+        }
+        const long long t0 = clock64();
+        for (;;) {
+          int seen = 0;
+          if (lane == 0) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.gn_ticket + b0) : "memory");
+          seen = __shfl_sync(0xffffffffu, seen, 0);
+          if (seen >= p.tiles_per_sample) break;
+          if (b0n < p.B && pub == it + 1) {
+            int ready = 0;
+            if (lane == 0) ready = mbar_try_wait(gn_stat_bar(slot ^ 1), static_cast<uint32_t>((it + 1) >> 1) & 1u) ? 1 : 0;
+            if (__shfl_sync(0xffffffffu, ready, 0)) {
+              publish(b0n);
+              pub = it + 2;
+            }
+          }
+          __nanosleep(32);
+          // The plan guarantees (host side, evc_gemm_plan_create) that no CTA waits for a third tile of a sample it
+          // owns and that the whole grid fits on the device at once, so the other tiles are being computed and this
+          // wait ends; foreign work holding SMs only delays it.  After ~10 s at any clock the caller broke the
+          // contract (tickets not zeroed): count a fault and carry on with the statistics that are there -- wrong
+          // numbers for this sample, reported through evc_gemm_fault_count(), instead of a hung or trapped context.
+          if (__shfl_sync(0xffffffffu, (clock64() - t0 > (1ll << 34)) ? 1 : 0, 0)) {
+            if (lane == 0) atomicAdd(&g_gn_wait_faults, 1u);
+            break;
+          }
+        }
+        __syncwarp();
+        mbar_wait(gn_free_bar(slot), par ^ 1u);  // pass 2 of the tile two iterations back has read this buffer
+        // raw channel sums of the tile's columns go through the coefficient buffer itself (one L2 round trip for the
+        // whole tile); a group that straddles the tile's column range reads its outside channels from L2 directly
+        float2* scoef = scoef_all + slot * p.BN;
+        const long long srow = (long long)b0 * p.N;
+        for (int j = lane; j < p.BN; j += 32) {
+          float2 t = make_float2(0.f, 0.f);
+          if (n0 + j < p.N) {
+            const longlong2 st = __ldcg(reinterpret_cast<const longlong2*>(p.stats + (srow + n0 + j) * 2));
+            t = make_float2((float)((double)st.x * (1.0 / 1048576.0)), (float)((double)st.y * (1.0 / 1048576.0)));
+          }
+          scoef[j] = t;
+        }
+        __syncwarp();
+        float ca[8], cb[8];  // BN <= 256: at most 8 columns per lane
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = lane + 32 * i;
+          const int c = n0 + j;
+          ca[i] = 0.f;
+          cb[i] = 0.f;
+          if (j < p.BN && c < p.N) {
+            const int g0 = (c / p.gn_cpg) * p.gn_cpg;
+            float sm = 0.f, qq = 0.f;
+            for (int k = 0; k < p.gn_cpg; ++k) {
+              const int jj = g0 + k - n0;
+              float2 t;
+              if (jj >= 0 && jj < p.BN) {
+                t = scoef[jj];
+              } else {
+                const longlong2 st = __ldcg(reinterpret_cast<const longlong2*>(p.stats + (srow + g0 + k) * 2));
+                t = make_float2((float)((double)st.x * (1.0 / 1048576.0)), (float)((double)st.y * (1.0 / 1048576.0)));
+              }
+              sm += t.x;
+              qq += t.y;
+            }
+            const float mean = sm * p.gn_inv_n;
+            const float var = fmaxf(qq * p.gn_inv_n - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + p.gn_eps);
+            ca[i] = rstd * (p.gn_adagn ? 1.f + __ldg(p.gn_ss + c) : __ldg(p.gn_ss + c));
+            cb[i] = __ldg(p.gn_ss + p.N + c) - mean * ca[i];
+          }
+        }
+        __syncwarp();  // every lane has read the raw sums
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (lane + 32 * i < p.BN) scoef[lane + 32 * i] = make_float2(ca[i], cb[i]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gn_coef_bar(slot));
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     // Per tile: (1) while the main loop of this tile is still running, stage the bias slice in smem and
@@ -382,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     // cross-thread synchronisation is needed for it); (2) wait for the accumulator; (3) TMEM -> registers ->
     // +bias +residual, *alpha -> global.
     const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int grp = (warp - 4) >> 2;   // 0/1: which 32-column chunks (even/odd) this warp handles
+    const int grp = (warp - 4) >> 2;   // which 32-column chunks this warp handles: grp, grp + kEpiGroups, ...
     const int row = q * 32 + lane;
     const int e = threadIdx.x - 128;  // 0..kEpiThreads-1
     const int dx = row % p.TW;
@@ -390,7 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     const int db = row / (p.TW * p.TH);
     uint8_t* gsm = smem_raw + (base - smem_u32(smem_raw));
     uint8_t* tail = gsm + (bar_base - base);
-    float* sbias = reinterpret_cast<float*>(tail + 256);
+    float* sbias_all = reinterpret_cast<float*>(tail + 256);
     const uint32_t res_pitch = static_cast<uint32_t>(p.BN) * 2u + 16u;
     uint8_t* sres = tail + p.off_resid + static_cast<size_t>(row) * res_pitch;
     const uint32_t sres_u32 = bar_base + p.off_resid + static_cast<uint32_t>(row) * res_pitch;
@@ -404,54 +550,17 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     // fused GroupNorm apply: two tile-sized slots (bf16, TMA-store layout) replace the per-warp staging buffers
     uint8_t* stg_base0 = tail + p.off_stage;
     bool gn_pending = false;
-    int gn_b = 0, gn_n0 = 0;
+    int gn_n0 = 0;
     long long gn_pix = 0;
-    auto gn_pass2 = [&](int pb, int pn0, long long ppix, int slot_idx) {
-      if (e == 0) {  // every tile of the sample has added its statistics?
-        int seen;
-        const long long t0 = clock64();
-        do {
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.gn_ticket + pb) : "memory");
-          if (seen < p.tiles_per_sample) {
-            __nanosleep(64);
-            // The plan guarantees (host side, evc_gemm_plan_create) that no CTA waits for a tile it owns itself and
-            // that the whole grid fits on the device at once, so the other tiles are being computed and this wait ends;
-            // foreign work holding SMs only delays it.  After ~10 s at any clock the caller broke the contract (tickets
-            // not zeroed): count a fault and carry on with the statistics that are there -- wrong numbers for this
-            // sample, reported through evc_gemm_fault_count(), instead of a hung or trapped context.
-            if (clock64() - t0 > (1ll << 34)) {
-              atomicAdd(&g_gn_wait_faults, 1u);
-              break;
-            }
-          }
-        } while (seen < p.tiles_per_sample);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      float2* scoef = reinterpret_cast<float2*>(sstat);  // the statistics scratch is free between tiles
-      for (int j = e; j < p.BN; j += kEpiThreads) {
-        const int c = pn0 + j;
-        float a = 0.f, bb = 0.f;
-        if (c < p.N) {
-          const int g0 = (c / p.gn_cpg) * p.gn_cpg;
-          float s = 0.f, qq = 0.f;
-          for (int k = 0; k < p.gn_cpg; ++k) {
-            const longlong2 st = __ldcg(reinterpret_cast<const longlong2*>(p.stats + ((long long)pb * p.N + g0 + k) * 2));
-            s += (float)((double)st.x * (1.0 / 1048576.0));
-            qq += (float)((double)st.y * (1.0 / 1048576.0));
-          }
-          const float mean = s * p.gn_inv_n;
-          const float var = fmaxf(qq * p.gn_inv_n - mean * mean, 0.f);
-          const float rstd = rsqrtf(var + p.gn_eps);
-          a = rstd * (p.gn_adagn ? 1.f + __ldg(p.gn_ss + c) : __ldg(p.gn_ss + c));
-          bb = __ldg(p.gn_ss + p.N + c) - mean * a;
-        }
-        scoef[j] = make_float2(a, bb);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float2* scoef_all = reinterpret_cast<const float2*>(tail + p.off_coef);
+    auto gn_pass2 = [&](int pn0, long long ppix, int pit) {  // pit: iteration index of the parked tile
+      const int slot_idx = pit & 1;
+      mbar_wait(gn_coef_bar(slot_idx), static_cast<uint32_t>(pit >> 1) & 1u);  // coordinator: (a, b) of this tile's columns
+      const float2* scoef = scoef_all + slot_idx * p.BN;
       uint8_t* slot = stg_base0 + static_cast<uint32_t>(slot_idx) * static_cast<uint32_t>(p.BN) * 256u;
       const uint32_t slot_u32 = bar_base + p.off_stage + static_cast<uint32_t>(slot_idx) * static_cast<uint32_t>(p.BN) * 256u;
       const int sw = (lane >> 1) & 3;
-      for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
+      for (int c0 = grp * 32; c0 < p.BN; c0 += kChunkStride) {
         const uint32_t boff = static_cast<uint32_t>((c0 >> 5) * 4 + q) * 2048u;
         uint8_t* srow = slot + boff + lane * 64;
 #pragma unroll
@@ -481,10 +590,16 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           bulk_commit();
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // scoef (= sstat) may be overwritten by the next tile's pass 1
+      __syncwarp();
+      if (lane == 0) mbar_arrive(gn_free_bar(slot_idx));  // this warp is done with the coefficient buffer
     };
+    // the bias vector (tiles_n * BN floats, zero beyond N) is staged once per CTA
+    if (p.bias != nullptr)
+      for (int j = e; j < p.tiles_n * p.BN; j += kEpiThreads) sbias_all[j] = (j < p.N) ? __ldg(p.bias + j) : 0.f;
+    epi_bar();
     int it = 0;
-    PROF_DECL(long long w_tfull = 0; long long w_pre = 0; long long w_ld = 0; long long w_rest = 0;)
+    PROF_DECL(long long w_tfull = 0; long long w_pre = 0; long long w_ld = 0; long long w_rest = 0; long long w_bw = 0;
+              long long w_st = 0; long long w_stat = 0;)
     PROF_T0(t_epi);
     int rit = 0;  // residual tiles fetched by TMA so far (phase of resid_bar)
     volatile int* sk_flag = reinterpret_cast<volatile int*>(tail + 192);  // free bytes of the barrier block
@@ -503,23 +618,34 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
       bool from_ws = false;
       const float* ws_row = nullptr;
+#ifdef EVC_GEMM_PROF
+      if (p.exp_skip & 16) {  // timing experiment: the epilogue only hands the accumulator back
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+          else mbar_arrive(tempty_bar(acc));
+        }
+        continue;
+      }
+#endif
       if (p.split_k > 1) {
         // ---- split-K, phase A (every unit): accumulator -> this K slice's fp32 plane, one ticket per (tile, CTA rank)
         const int ks = u - tile * p.split_k;
         const long long tm = (long long)(tile / p.tiles_n) * CG + rank;
-        float* wrow = p.sk_ws + (long long)ks * p.sk_plane + (tm * 128 + row) * p.sk_ld + n0;
-        ws_row = p.sk_ws + (tm * 128 + row) * p.sk_ld + n0;
+        // plane layout [M tile][column][128 rows]: the 32 lanes of a warp (= 32 rows) write / read 128 contiguous bytes
+        float* wrow = p.sk_ws + (long long)ks * p.sk_plane + (tm * p.sk_ld + n0) * 128 + row;
+        ws_row = p.sk_ws + (tm * p.sk_ld + n0) * 128 + row;
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {  // BN % 32 == 0 (checked by the host)
+        for (int c0 = grp * 32; c0 < p.BN; c0 += kChunkStride) {  // BN % 32 == 0 (checked by the host)
           uint32_t v[32];
           tmem_ld_32x32(taddr + c0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            __stcg(reinterpret_cast<float4*>(wrow + c0 + j),
-                   make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                               __uint_as_float(v[j + 3])));
+          for (int j = 0; j < 32; ++j) __stcg(wrow + (c0 + j) * 128, __uint_as_float(v[j]));
         }
         tc_fence_before();
         __syncwarp();
@@ -528,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           else mbar_arrive(tempty_bar(acc));
         }
         __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        epi_bar();
         if (e == 0) {
           int* tk = p.sk_ticket + (long long)tile * CG + rank;
           const int seen = atomicAdd(tk, 1);
@@ -536,17 +662,15 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           if (last) *tk = 0;  // every slice has arrived: ready for the next launch
           *sk_flag = last;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        epi_bar();
         if (*sk_flag == 0) continue;  // another unit adds the slices up
         __threadfence();
         from_ws = true;
       }
       // (1) prefetch
       PROF_T0(t_pre);
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone is done with the previous tile's sbias
-      if (p.bias != nullptr) {
-        for (int j = e; j < p.BN; j += kEpiThreads) sbias[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
-      }
+      epi_bar();  // everyone is done with the previous tile's residual rows and statistics scratch
+      const float* sbias = sbias_all + n0;
       if (p.resid_tma) {
         if (warp == 4 && elect_one()) {
           const int panels = (p.BN + 63) >> 6;
@@ -558,14 +682,13 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         }
       } else if (resid_fast && valid) {
         const __nv_bfloat16* r = p.resid + pix * p.resid_ld + n0;
-        for (int c0 = grp * 32; c0 < p.BN; c0 += 64)  // only the chunks this thread will consume
+        for (int c0 = grp * 32; c0 < p.BN; c0 += kChunkStride)  // only the chunks this thread will consume
 #pragma unroll
           for (int j = c0; j < c0 + 32; j += 8)
             if (j < p.BN)
               asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sres_u32 + j * 2), "l"(r + j) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // sbias visible
       PROF_ADD(w_pre, t_pre);
       // (2) accumulator ready
       PROF_T0(t_tf);
@@ -590,11 +713,11 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         uint8_t* slot = stg_base0 + static_cast<uint32_t>(it & 1) * static_cast<uint32_t>(p.BN) * 256u;
         if (elect_one()) bulk_wait_read<0>();  // the stores that read this slot were issued a whole tile ago
         __syncwarp();
-        for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
+        for (int c0 = grp * 32; c0 < p.BN; c0 += kChunkStride) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c0, v);
           tmem_ld_wait();
-          if (c0 + 64 >= p.BN) {
+          if (c0 + kChunkStride >= p.BN) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -635,7 +758,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
           if (lane < 16) *reinterpret_cast<float4*>(sstat + (q * p.BN + c0 + 2 * cp) * 2) = make_float4(s0, q0, s1, q1);
         }
-        if (p.BN <= 32 && grp == 1) {  // this warp had no chunk: it still owes the accumulator release
+        if (grp * 32 >= p.BN) {  // this warp had no chunk: it still owes the accumulator release
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -643,7 +766,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
             else mbar_arrive(tempty_bar(acc));
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        epi_bar();
         if (tile_ok) {
           for (int i = e; i < 2 * p.BN; i += kEpiThreads) {
             const int col = i >> 1;
@@ -653,19 +776,16 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
             }
           }
         }
-        __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (e == 0 && tile_ok)
-          asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p.gn_ticket + b0), "r"(1) : "memory");
-        if (gn_pending) gn_pass2(gn_b, gn_n0, gn_pix, (it & 1) ^ 1);
+        __syncwarp();
+        if (tile_ok && lane == 0) mbar_arrive(gn_stat_bar(it & 1));  // the coordinator publishes the sample ticket
+        if (gn_pending) gn_pass2(gn_n0, gn_pix, it - 1);
         gn_pending = tile_ok;
-        gn_b = b0;
         gn_n0 = n0;
         gn_pix = ((long long)b0 * p.H + y0) * p.W + x0;
         continue;
       }
       bool released = from_ws;  // split-K: the accumulator was handed back in phase A
-      for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
+      for (int c0 = grp * 32; c0 < p.BN; c0 += kChunkStride) {
         const int ncols = min(32, p.BN - c0);
         uint32_t v[32];
         PROF_T0(t_ld);
@@ -675,15 +795,9 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) sacc[j] = 0.f;
           for (int ks = 0; ks < p.split_k; ++ks) {
-            const float* src = ws_row + (long long)ks * p.sk_plane + c0;
+            const float* src = ws_row + (long long)ks * p.sk_plane + c0 * 128;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + j));
-              sacc[j] += t4.x;
-              sacc[j + 1] += t4.y;
-              sacc[j + 2] += t4.z;
-              sacc[j + 3] += t4.w;
-            }
+            for (int j = 0; j < 32; ++j) sacc[j] += __ldcg(src + j * 128);
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(sacc[j]);
@@ -696,7 +810,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         }
         PROF_ADD(w_ld, t_ld);
         PROF_T0(t_rest);
-        if (!from_ws && c0 + 64 >= p.BN) {
+        if (!from_ws && c0 + kChunkStride >= p.BN) {
           released = true;
           // last TMEM read of this tile is complete: hand the accumulator stage back to the MMA warp
           tc_fence_before();
@@ -761,11 +875,14 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           }
           const uint32_t boff = (p.tma_out == 2 ? static_cast<uint32_t>(stg_i & 1) : 0u) * 2048u;
           ++stg_i;
+          PROF_T0(t_bw);
           if (elect_one()) {  // the TMA unit must have finished reading this buffer (store issued two / one chunks ago)
             if (p.tma_out == 2) bulk_wait_read<1>();
             else bulk_wait_read<0>();
           }
           __syncwarp();
+          PROF_ADD(w_bw, t_bw);
+          PROF_T0(t_st);
           uint8_t* srow = stg_base + boff + lane * 64;
           const int sw = (lane >> 1) & 3;
 #pragma unroll
@@ -784,6 +901,8 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
             tma_store_2d(&p.out_map, stg_base_u32 + boff, n, static_cast<int>(tile_pix) + q * 32);
             bulk_commit();
           }
+          PROF_ADD(w_st, t_st);
+          PROF_T0(t_stat);
           if (p.stats != nullptr) {
             // column sums of the values as stored, read back from the staging buffer: lane -> (row parity, column
             // pair); 16 conflict-free 4-byte loads per lane, then one exchange between the two parities
@@ -822,6 +941,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
               }
             }
           }
+          PROF_ADD(w_stat, t_stat);
           PROF_ADD(w_rest, t_rest);
           continue;
         }
@@ -905,7 +1025,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         }
         PROF_ADD(w_rest, t_rest);
       }
-      if (!released) {  // this warp had no chunk in this tile (BN <= 32 and grp == 1)
+      if (!released) {  // this warp had no chunk in this tile (BN <= 32 * grp)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -914,7 +1034,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         }
       }
       if (p.stats != nullptr && p.stats_combine) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        epi_bar();
         if (b0 < p.B) {
           for (int i = e; i < 2 * p.BN; i += kEpiThreads) {
             const int col = i >> 1;
@@ -926,7 +1046,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         }
       }
     }
-    if (!SPLIT && p.gn_fuse && gn_pending) gn_pass2(gn_b, gn_n0, gn_pix, (it & 1) ^ 1);  // `it` = tiles done
+    if (!SPLIT && p.gn_fuse && gn_pending) gn_pass2(gn_n0, gn_pix, it - 1);  // `it` = tiles done
     __syncwarp();
     if (p.tma_out != 0 && elect_one()) bulk_wait_all();  // staging buffers are read before the CTA's smem goes away
 #ifdef EVC_GEMM_PROF
@@ -938,6 +1058,9 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       PROF_OUT(8, w_pre);
       PROF_OUT(9, w_ld);
       PROF_OUT(10, w_rest);
+      PROF_OUT(11, w_bw);
+      PROF_OUT(12, w_st);
+      PROF_OUT(13, w_stat);
     }
 #endif
   }
@@ -1188,7 +1311,7 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   if (p.resid_tma) p.resid_smem = 0;
   // scratch behind the barrier block: [barriers 256 B][bias 1 KB][residual][statistics][store staging]
   auto layout = [&](int nbuf) {
-    int off = 256 + 1024;
+    int off = 256 + ((p.tiles_n * d->bn * 4 + 255) & ~255);  // barriers, then the whole bias vector
     if (p.resid_tma) {
       off = (off + 1023) & ~1023;
       p.off_resid = off;
@@ -1199,17 +1322,20 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     }
     p.off_stat = off;
     if (d->stats) off += 32 * d->bn;
+    p.off_coef = off;
+    if (d->gn_ss != nullptr) off += 2 * d->bn * 8;  // two coefficient buffers
     if (nbuf > 0) {
       off = (off + 1023) & ~1023;
       p.off_stage = off;
       // fused GroupNorm apply: two whole-tile slots (bn x 256 B each) instead of the per-warp staging buffers
-      off += (d->gn_ss != nullptr) ? 2 * d->bn * 256 : 8 * nbuf * 2048;
+      off += (d->gn_ss != nullptr) ? 2 * d->bn * 256 : (kEpiThreads / 32) * nbuf * 2048;
     }
     return off;
   };
   p.tma_out = 0;
 #ifdef EVC_GEMM_PROF
   p.exp_alt = getenv("EVC_EXP_ALT") ? atoi(getenv("EVC_EXP_ALT")) : 0;
+  p.exp_skip = getenv("EVC_EXP_SKIP") ? atoi(getenv("EVC_EXP_SKIP")) : 0;
 #endif
   if (can_tma_out) {
     uint64_t dims[2] = {(uint64_t)d->w_rows, (uint64_t)m_total};
@@ -1300,6 +1426,10 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     delete pl;
     return evc_set_error(EVC_ERR_INVALID, "tile does not fit in shared memory");
   }
+#ifdef EVC_GEMM_PROF
+  if (getenv("EVC_EXP_STAGES") && atoi(getenv("EVC_EXP_STAGES")) >= 2 && atoi(getenv("EVC_EXP_STAGES")) < stages)
+    stages = atoi(getenv("EVC_EXP_STAGES"));
+#endif
   p.num_stages = stages;
   pl->smem_bytes = stages * stage_bytes + 1024 + tail_bytes;
 

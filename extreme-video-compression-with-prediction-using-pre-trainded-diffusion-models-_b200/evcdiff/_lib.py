@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libevcdiff.so")
+# EVC_LIB: another build of the same library (tools/build_prof.sh: the wait-time probe build, experiments only)
+LIB_PATH = os.environ.get("EVC_LIB") or os.path.join(_HERE, "lib", "libevcdiff.so")
 
 EVC_OUT_BF16_ROWS, EVC_OUT_F32_ROWS, EVC_OUT_BF16_T, EVC_OUT_F32_T = 0, 1, 2, 3
 

@@ -228,7 +228,7 @@ def pick_tile(n, mt, kblocks, sms=None, allow_split=True):
     cands = [bn for bn in (256, 192, 128, 96, 64, 48, 32, 16) if n % bn == 0]
     if not cands:
         return pick_bn(n, mt, kblocks, sms), 1
-    best = None
+    best1, bests = None, None  # best unsplit / best split candidate: (cost, bn, S)
     for bn in cands:
         tiles = mt * (n // bn)
         cg = 2 if ((mt + 1) // 2) * (n // bn) >= 2 * (sms // 2) and bn % 16 == 0 else 1
@@ -239,12 +239,18 @@ def pick_tile(n, mt, kblocks, sms=None, allow_split=True):
                 continue
             waves = -(-(tiles * S) // sms)
             cost = waves * (-(-kblocks // S) * per_kb + 1500 + 12 * bn)
-            if S > 1:
-                cost += 8 * S * bn + 2500  # last arriver re-reads the S partial tiles; ticket round trip
-            key = (cost * (1.0 if best is None else 1.0), -bn)
-            if best is None or cost < best[0] * 0.97:  # prefer wider tiles / fewer slices unless clearly slower
-                best = (cost, bn, S)
-    return best[1], best[2]
+            if S == 1:
+                if best1 is None or cost < best1[0] * 0.97:  # prefer wider tiles unless clearly slower
+                    best1 = (cost, bn, 1)
+            else:
+                # partial tiles through L2, ticket round trip, the last arriver adds S slices alone: measured 6-8 us per
+                # launch (gpurun_out r2d / r2e profiles), so a split has to remove a lot of K-loop time to pay
+                cost += 14000 + 900 * S * (bn // 32)
+                if bests is None or cost < bests[0] * 0.97:
+                    bests = (cost, bn, S)
+    if bests is not None and bests[0] < 0.8 * best1[0]:
+        return bests[1], bests[2]
+    return pick_bn(n, mt, kblocks, sms), 1
 
 
 def gn_fuse_fits(sample_m_tiles, m_tiles_total, tiles_n, sms=None):

