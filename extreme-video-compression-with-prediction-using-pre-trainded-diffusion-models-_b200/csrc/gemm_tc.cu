@@ -209,8 +209,9 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, const float (&f
 
 template <int CG, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_constant__ GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0u) __trap();  // the host sizes the allocation without alignment slack
   // warp index through a shuffle: the compiler then knows it is warp-uniform, so the producer / MMA loops below are
   // convergent code whose descriptors live in uniform registers (a `lane == 0` loop makes ptxas wrap every
   // UTMALDG / UTCHMMA / UTCBAR in an ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall loop)
@@ -408,115 +409,99 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       PROF_OUT(2, w_tempty);
       PROF_OUT(7, 1);
     }
-  } else if (warp == 3) {
-    // ------------------------------------------------------------------ fused GroupNorm apply: coordinator.
-    // Everything that waits for global memory is kept off the epilogue warps: for each tile of this CTA, once the
-    // epilogue has issued the tile's statistics (gn_stat_bar), publish one ticket for the sample, wait until every tile
-    // of the sample has published its own, fetch the sample's channel sums once (one L2 round trip), turn them into
-    // per-column (a, b) with y = a * x + b, and hand them to the epilogue's pass 2 (gn_coef_bar).
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ fused GroupNorm apply: ticket publisher.
+    // Warps 2 and 3 keep everything that waits for global memory off the epilogue warps.  This one turns "the epilogue
+    // has issued the statistics of tile k" (gn_stat_bar) into one ticket for the tile's sample, as early as possible: a
+    // sample is complete for everybody only when its last ticket is out.
     if (!SPLIT && p.gn_fuse) {
-      uint8_t* tail3 = smem_raw + (bar_base - smem_u32(smem_raw));
-      float2* scoef_all = reinterpret_cast<float2*>(tail3 + p.off_coef);
       int it = 0;
-      int pub = 0;  // tickets of this CTA's tiles [0, pub) are published
-      // the statistics atomics of the epilogue threads happen before their arrivals on gn_stat_bar, which this warp has
-      // observed: the fence makes them visible device-wide before the ticket is
-      auto publish = [&](int b) {
-        if (lane == 0) {
-          __threadfence();
-          asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p.gn_ticket + b), "r"(1) : "memory");
-        }
-      };
       for (int u = unit; u < total_units; u += num_units, ++it) {
         int x0, y0, b0, n0;
         decode_tile<CG>(p, u, rank, x0, y0, b0, n0);
         if (b0 >= p.B) continue;  // the peer CTA of an odd last pair has no tile
+        mbar_wait(gn_stat_bar(it & 1), static_cast<uint32_t>(it >> 1) & 1u);
+        if (lane == 0) {
+          // the statistics atomics of the epilogue threads happen before their arrivals on gn_stat_bar, which this
+          // thread has observed: the fence makes them visible device-wide before the ticket is
+          __threadfence();
+          asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p.gn_ticket + b0), "r"(1) : "memory");
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ fused GroupNorm apply: coefficients.
+    // For each tile of this CTA: wait until every tile of its sample has published a ticket, fetch the channel sums of
+    // the tile's groups once (one L2 round trip), turn them into per-column (a, b) with y = a * x + b, and hand them
+    // to the epilogue's pass 2 (gn_coef_bar).  A sample's tiles are spread over two rounds of the persistent grid, so
+    // the latency of this chain (statistics -> ticket -> poll -> sums -> coefficients) is paid once per round by the
+    // CTAs that hold a sample's early tiles: it is kept as short as measured variants allow (profiles/r02_notes.md).
+    if (!SPLIT && p.gn_fuse) {
+      uint8_t* tail3 = smem_raw + (bar_base - smem_u32(smem_raw));
+      float2* scoef_all = reinterpret_cast<float2*>(tail3 + p.off_coef);
+      float2* sraw = scoef_all + 2 * p.BN;                          // raw sums of <= BN + 2 * 48 channels
+      float* sgn = reinterpret_cast<float*>(sraw + p.BN + 96);      // [gamma' (N) | beta' (N)] of this launch's label
+      for (int j = lane; j < 2 * p.N; j += 32) sgn[j] = __ldg(p.gn_ss + j);
+      __syncwarp();
+      int it = 0;
+      for (int u = unit; u < total_units; u += num_units, ++it) {
+        int x0, y0, b0, n0;
+        decode_tile<CG>(p, u, rank, x0, y0, b0, n0);
+        if (b0 >= p.B) continue;
         const int slot = it & 1;
         const uint32_t par = (it >> 1) & 1u;
-        if (pub <= it) {
-          mbar_wait(gn_stat_bar(slot), par);
-          publish(b0);
-          pub = it + 1;
-        }
-        // the next tile may belong to the same sample: its ticket must go out while this one is being waited for
-        int b0n = p.B;
-        if (u + num_units < total_units) {
-          int xn, yn, nn;
-          decode_tile<CG>(p, u + num_units, rank, xn, yn, b0n, nn);
-        }
-        const long long t0 = clock64();
-        for (;;) {
-          int seen = 0;
-          if (lane == 0) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.gn_ticket + b0) : "memory");
-          seen = __shfl_sync(0xffffffffu, seen, 0);
-          if (seen >= p.tiles_per_sample) break;
-          if (b0n < p.B && pub == it + 1) {
-            int ready = 0;
-            if (lane == 0) ready = mbar_try_wait(gn_stat_bar(slot ^ 1), static_cast<uint32_t>((it + 1) >> 1) & 1u) ? 1 : 0;
-            if (__shfl_sync(0xffffffffu, ready, 0)) {
-              publish(b0n);
-              pub = it + 2;
+        mbar_wait(gn_stat_bar(slot), par);  // nothing to poll for before this CTA's own tile has reported
+        if (lane == 0) {
+          int seen;
+          const long long t0 = clock64();
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.gn_ticket + b0) : "memory");
+            if (seen < p.tiles_per_sample) {
+              __nanosleep(32);
+              // The plan guarantees (host side, evc_gemm_plan_create) that no CTA waits for a third tile of a sample
+              // it owns and that the whole grid fits on the device at once, so the other tiles are being computed and
+              // this wait ends; foreign work holding SMs only delays it.  After ~10 s at any clock the caller broke
+              // the contract (tickets not zeroed): count a fault and carry on with the statistics that are there --
+              // wrong numbers for this sample, reported through evc_gemm_fault_count(), instead of a hung or trapped
+              // context.
+              if (clock64() - t0 > (1ll << 34)) {
+                atomicAdd(&g_gn_wait_faults, 1u);
+                break;
+              }
             }
-          }
-          __nanosleep(32);
-          // The plan guarantees (host side, evc_gemm_plan_create) that no CTA waits for a third tile of a sample it
-          // owns and that the whole grid fits on the device at once, so the other tiles are being computed and this
-          // wait ends; foreign work holding SMs only delays it.  After ~10 s at any clock the caller broke the
-          // contract (tickets not zeroed): count a fault and carry on with the statistics that are there -- wrong
-          // numbers for this sample, reported through evc_gemm_fault_count(), instead of a hung or trapped context.
-          if (__shfl_sync(0xffffffffu, (clock64() - t0 > (1ll << 34)) ? 1 : 0, 0)) {
-            if (lane == 0) atomicAdd(&g_gn_wait_faults, 1u);
-            break;
-          }
+          } while (seen < p.tiles_per_sample);
         }
         __syncwarp();
         mbar_wait(gn_free_bar(slot), par ^ 1u);  // pass 2 of the tile two iterations back has read this buffer
-        // raw channel sums of the tile's columns go through the coefficient buffer itself (one L2 round trip for the
-        // whole tile); a group that straddles the tile's column range reads its outside channels from L2 directly
-        float2* scoef = scoef_all + slot * p.BN;
-        const long long srow = (long long)b0 * p.N;
-        for (int j = lane; j < p.BN; j += 32) {
-          float2 t = make_float2(0.f, 0.f);
-          if (n0 + j < p.N) {
-            const longlong2 st = __ldcg(reinterpret_cast<const longlong2*>(p.stats + (srow + n0 + j) * 2));
-            t = make_float2((float)((double)st.x * (1.0 / 1048576.0)), (float)((double)st.y * (1.0 / 1048576.0)));
-          }
-          scoef[j] = t;
+        const int c_lo = (n0 / p.gn_cpg) * p.gn_cpg;
+        const int c_end = min(n0 + p.BN, p.N);
+        const int c_hi = min(p.N, ((c_end + p.gn_cpg - 1) / p.gn_cpg) * p.gn_cpg);
+        for (int c = c_lo + lane; c < c_hi; c += 32) {
+          const longlong2 st = __ldcg(reinterpret_cast<const longlong2*>(p.stats + ((long long)b0 * p.N + c) * 2));
+          sraw[c - c_lo] = make_float2((float)((double)st.x * (1.0 / 1048576.0)), (float)((double)st.y * (1.0 / 1048576.0)));
         }
         __syncwarp();
-        float ca[8], cb[8];  // BN <= 256: at most 8 columns per lane
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int j = lane + 32 * i;
+        float2* scoef = scoef_all + slot * p.BN;
+        for (int j = lane; j < p.BN; j += 32) {
           const int c = n0 + j;
-          ca[i] = 0.f;
-          cb[i] = 0.f;
-          if (j < p.BN && c < p.N) {
-            const int g0 = (c / p.gn_cpg) * p.gn_cpg;
+          float a = 0.f, bb = 0.f;
+          if (c < p.N) {
+            const int g0 = (c / p.gn_cpg) * p.gn_cpg - c_lo;
             float sm = 0.f, qq = 0.f;
             for (int k = 0; k < p.gn_cpg; ++k) {
-              const int jj = g0 + k - n0;
-              float2 t;
-              if (jj >= 0 && jj < p.BN) {
-                t = scoef[jj];
-              } else {
-                const longlong2 st = __ldcg(reinterpret_cast<const longlong2*>(p.stats + (srow + g0 + k) * 2));
-                t = make_float2((float)((double)st.x * (1.0 / 1048576.0)), (float)((double)st.y * (1.0 / 1048576.0)));
-              }
+              const float2 t = sraw[g0 + k];
               sm += t.x;
               qq += t.y;
             }
             const float mean = sm * p.gn_inv_n;
             const float var = fmaxf(qq * p.gn_inv_n - mean * mean, 0.f);
             const float rstd = rsqrtf(var + p.gn_eps);
-            ca[i] = rstd * (p.gn_adagn ? 1.f + __ldg(p.gn_ss + c) : __ldg(p.gn_ss + c));
-            cb[i] = __ldg(p.gn_ss + p.N + c) - mean * ca[i];
+            a = rstd * (p.gn_adagn ? 1.f + sgn[c] : sgn[c]);
+            bb = sgn[p.N + c] - mean * a;
           }
+          scoef[j] = make_float2(a, bb);
         }
-        __syncwarp();  // every lane has read the raw sums
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (lane + 32 * i < p.BN) scoef[lane + 32 * i] = make_float2(ca[i], cb[i]);
         __syncwarp();
         if (lane == 0) mbar_arrive(gn_coef_bar(slot));
       }
@@ -1174,8 +1159,10 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     } else if (d->cta_group == 0 && can_pair) {
       // same-box A/B on B200 under the 1 kW cap (profiles/r01_notes.md): pairs are ~1.5 % faster end to end --
       // fewer B-tile bytes per FLOP lowers power, which raises the sustained clock
-      const long long pair_tiles = (long long)((p.m_tiles + 1) / 2) * p.tiles_n;
-      if (pair_tiles >= 2LL * (evc_num_sms() / 2)) cg = 2;
+      // r02 (gpurun_out r2j, same box, forced pairs vs the old "at least two rounds of pair tiles" rule): pairs also win
+      // 10-30 % on launches with few tiles (8x8 / 16x16 levels, small batches) -- half the B-operand traffic per SM and
+      // more pipeline stages in the same shared memory -- unless the M tiles cannot be paired up without waste
+      if (p.m_tiles >= 8 && ((p.m_tiles & 1) == 0 || p.m_tiles >= 23)) cg = 2;
     }
   }
   const int split_k = d->split_k > 1 ? d->split_k : 1;
@@ -1323,7 +1310,8 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     p.off_stat = off;
     if (d->stats) off += 32 * d->bn;
     p.off_coef = off;
-    if (d->gn_ss != nullptr) off += 2 * d->bn * 8;  // two coefficient buffers
+    // two coefficient buffers, raw sums of the tile's groups (cpg <= 48 checked below), the AdaGN row of the launch
+    if (d->gn_ss != nullptr) off += 2 * d->bn * 8 + (d->bn + 96) * 8 + 2 * d->w_rows * 4;
     if (nbuf > 0) {
       off = (off + 1023) & ~1023;
       p.off_stage = off;
@@ -1352,7 +1340,7 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
       return rc;
     }
     // two staging buffers per epilogue warp unless that would leave fewer than four pipeline stages
-    p.tma_out = (tma_env >= 2 && (227 * 1024 - 1024 - layout(2)) / stage_bytes >= 4) ? 2 : 1;
+    p.tma_out = (tma_env >= 2 && (227 * 1024 - layout(2)) / stage_bytes >= 4) ? 2 : 1;
   }
   p.split_k = 1;
   if (split_k > 1) {
@@ -1376,7 +1364,7 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   if (d->gn_ss != nullptr) {
     const bool ok = p.tma_out != 0 && d->stats != nullptr && d->gn_ticket != nullptr && d->bias != nullptr &&
                     d->resid == nullptr && d->alpha == 1.0f && TW * TH == 128 && d->gn_groups > 0 &&
-                    (d->w_rows % d->gn_groups) == 0 && d->max_ctas <= 0;
+                    (d->w_rows % d->gn_groups) == 0 && d->w_rows / d->gn_groups <= 48 && d->max_ctas <= 0;
     if (!ok) {
       delete pl;
       return evc_set_error(EVC_ERR_INVALID,
@@ -1419,7 +1407,7 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     p.tiles_per_sample = p.tiles_x * p.tiles_y * p.tiles_n;
   }
   const int tail_bytes = layout(p.tma_out);
-  const int budget = 227 * 1024 - 1024 /*align slack*/ - tail_bytes;
+  const int budget = 227 * 1024 - tail_bytes;  // the kernel's dynamic shared memory is declared 1024-byte aligned
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
@@ -1431,7 +1419,7 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
     stages = atoi(getenv("EVC_EXP_STAGES"));
 #endif
   p.num_stages = stages;
-  pl->smem_bytes = stages * stage_bytes + 1024 + tail_bytes;
+  pl->smem_bytes = stages * stage_bytes + tail_bytes;
 
   const long long units = (long long)((p.m_tiles + cg - 1) / cg) * p.tiles_n * p.split_k;  // (tile | tile pair) x K slice
   int sms = evc_num_sms();

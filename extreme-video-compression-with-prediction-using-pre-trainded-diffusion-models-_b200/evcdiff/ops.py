@@ -231,7 +231,7 @@ def pick_tile(n, mt, kblocks, sms=None, allow_split=True):
     best1, bests = None, None  # best unsplit / best split candidate: (cost, bn, S)
     for bn in cands:
         tiles = mt * (n // bn)
-        cg = 2 if ((mt + 1) // 2) * (n // bn) >= 2 * (sms // 2) and bn % 16 == 0 else 1
+        cg = 2 if (mt >= 8 and (mt % 2 == 0 or mt >= 23) and bn % 16 == 0) else 1  # mirrors evc_gemm_plan_create
         per_kb = max(2 * bn, TMA_CYCLES_PER_ROW * (128 + bn / cg))
         for S in (1, 2, 3, 4, 6, 8, 12, 16):
             if S > 1 and (bn % 32 != 0 or kblocks // S < 4 or tiles * S > sms or
