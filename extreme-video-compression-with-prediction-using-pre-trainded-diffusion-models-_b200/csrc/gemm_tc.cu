@@ -122,6 +122,7 @@ struct alignas(64) GemmParams {
   int* sk_ticket;          // [total_tiles * CG], zero before the first launch; reset by the last arriver
   long long sk_plane;      // elements per K-slice plane
   int sk_ld;               // tiles_n * BN
+  int sk_coop;             // 1: every unit is resident (grid == units): each K slice's CTA finishes the chunks it owns
 };
 
 // Work unit `tile` of a CTA (CG = 1) or CTA pair (CG = 2): N tile tn = tile % tiles_n, M tile(s) CG*(tile/tiles_n)+rank.
@@ -603,6 +604,8 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
       bool from_ws = false;
       const float* ws_row = nullptr;
+      int sk_ks = 0;
+      int* sk_tk = nullptr;
 #ifdef EVC_GEMM_PROF
       if (p.exp_skip & 16) {  // timing experiment: the epilogue only hands the accumulator back
         mbar_wait(tfull_bar(acc), acc_phase);
@@ -640,18 +643,35 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         }
         __threadfence();
         epi_bar();
-        if (e == 0) {
-          int* tk = p.sk_ticket + (long long)tile * CG + rank;
-          const int seen = atomicAdd(tk, 1);
-          const int last = (seen == p.split_k - 1) ? 1 : 0;
-          if (last) *tk = 0;  // every slice has arrived: ready for the next launch
-          *sk_flag = last;
+        sk_ks = ks;
+        sk_tk = p.sk_ticket + (long long)tile * CG + rank;
+        if (p.sk_coop) {
+          // every slice of the tile is being computed right now (grid == units, one CTA per SM): wait for all of them,
+          // then this CTA finishes the 32-column chunks it owns (chunk index % split_k == ks) -- the S-fold reduction
+          // and the epilogue run on S SMs instead of on the last arriver alone.  The ticket counts arrivals (0..S) and
+          // then departures (S..2S); the last one to leave zeroes it for the next launch.
+          if (e == 0) {
+            atomicAdd(sk_tk, 1);
+            int seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(sk_tk) : "memory");
+            } while (seen < p.split_k);
+          }
+          epi_bar();
+        } else {
+          if (e == 0) {
+            const int seen = atomicAdd(sk_tk, 1);
+            const int last = (seen == p.split_k - 1) ? 1 : 0;
+            if (last) *sk_tk = 0;  // every slice has arrived: ready for the next launch
+            *sk_flag = last;
+          }
+          epi_bar();
+          if (*sk_flag == 0) continue;  // another unit adds the slices up
+          __threadfence();
         }
-        epi_bar();
-        if (*sk_flag == 0) continue;  // another unit adds the slices up
-        __threadfence();
         from_ws = true;
       }
+      const bool sk_owned_only = from_ws && p.sk_coop;
       // (1) prefetch
       PROF_T0(t_pre);
       epi_bar();  // everyone is done with the previous tile's residual rows and statistics scratch
@@ -771,11 +791,12 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       }
       bool released = from_ws;  // split-K: the accumulator was handed back in phase A
       for (int c0 = grp * 32; c0 < p.BN; c0 += kChunkStride) {
+        if (sk_owned_only && ((c0 >> 5) % p.split_k) != sk_ks) continue;  // another slice's CTA finishes this chunk
         const int ncols = min(32, p.BN - c0);
         uint32_t v[32];
         PROF_T0(t_ld);
         if (from_ws) {
-          // split-K, phase B (last arriver): slices added in the fixed order 0, 1, ..., split_k-1
+          // split-K, phase B: slices added in the fixed order 0, 1, ..., split_k-1
           float sacc[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) sacc[j] = 0.f;
@@ -1023,12 +1044,16 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
         if (b0 < p.B) {
           for (int i = e; i < 2 * p.BN; i += kEpiThreads) {
             const int col = i >> 1;
-            if (n0 + col < p.N) {
+            if (n0 + col < p.N && !(sk_owned_only && ((col >> 5) % p.split_k) != sk_ks)) {
               const float t = sstat[i] + sstat[2 * p.BN + i] + sstat[4 * p.BN + i] + sstat[6 * p.BN + i];
               stat_add(p.stats + ((long long)b0 * p.N + n0 + col) * 2 + (i & 1), t);
             }
           }
         }
+      }
+      if (sk_owned_only) {  // departure: the last CTA to leave the tile zeroes its ticket for the next launch
+        epi_bar();
+        if (e == 0 && atomicAdd(sk_tk, 1) == 2 * p.split_k - 1) *sk_tk = 0;
       }
     }
     if (!SPLIT && p.gn_fuse && gn_pending) gn_pass2(gn_n0, gn_pix, it - 1);  // `it` = tiles done
@@ -1426,6 +1451,7 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   int cap = (d->max_ctas > 0 ? d->max_ctas : sms) / cg;
   if (cap < 1) cap = 1;
   pl->grid = cg * (int)(units < cap ? units : cap);
+  p.sk_coop = (p.split_k > 1 && units <= cap) ? 1 : 0;  // every K slice of every tile on its own resident CTA (pair)
   pl->flops = 2.0 * (double)d->B * d->H * d->W * (double)d->w_rows * (double)d->w_k;
   *out_plan = pl;
   return EVC_OK;

@@ -238,14 +238,16 @@ def pick_tile(n, mt, kblocks, sms=None, allow_split=True):
                           S * ((mt + 1) // 2 * 2) * 128 * n * 4 > SPLIT_K_WS_BYTES):
                 continue
             waves = -(-(tiles * S) // sms)
-            cost = waves * (-(-kblocks // S) * per_kb + 1500 + 12 * bn)
+            pk = per_kb if S == 1 else max(2 * bn, TMA_CYCLES_PER_ROW * (128 + bn))  # split launches run unpaired
+            cost = waves * (-(-kblocks // S) * pk + 1500 + 12 * bn)
             if S == 1:
                 if best1 is None or cost < best1[0] * 0.97:  # prefer wider tiles unless clearly slower
                     best1 = (cost, bn, 1)
             else:
-                # partial tiles through L2, ticket round trip, the last arriver adds S slices alone: measured 6-8 us per
-                # launch (gpurun_out r2d / r2e profiles), so a split has to remove a lot of K-loop time to pay
-                cost += 14000 + 900 * S * (bn // 32)
+                # partial tiles through L2 + one ticket round trip
+                # cooperative finish (tiles * S <= SMs, so every slice is resident): each slice's CTA reduces and stores
+                # the chunks it owns
+                cost += 9000 + 150 * S * max(1, (bn // 32) // S)
                 if bests is None or cost < bests[0] * 0.97:
                     bests = (cost, bn, S)
     if bests is not None and bests[0] < 0.8 * best1[0]:

@@ -14,13 +14,20 @@ from .pipeline import generate_frame
 
 
 class BatchedSender:
-    def __init__(self, net, config=None, threshold=20.0, sampler="DDPM", keyframe_fn=None, max_batch=64, **sampler_kwargs):
+    def __init__(self, net, config=None, threshold=20.0, sampler="DDPM", keyframe_fn=None, max_batch=64, compact=True,
+                 bucket=8, **sampler_kwargs):
         self.net = net
         self.config = config or net.config
         self.threshold = threshold
         self.sampler = sampler
         self.keyframe_fn = keyframe_fn or (lambda frames_gt: frames_gt)  # ELIC stand-in: lossless keyframes
         self.max_batch = max_batch
+        # finished videos leave the sampling batch (the reference stops calling update() for a video that has its 30
+        # frames, city_sender.py:534); the active set is padded to a multiple of `bucket` so that only a few batch
+        # sizes (= engines / captured graphs) ever exist
+        self.compact = compact
+        self.bucket = max(1, int(bucket))
+        self.sampled_videos = 0  # videos x cycles actually sampled (diagnostic)
         self.sampler_kwargs = sampler_kwargs
         self.num_frames = self.config.data.num_frames
         self.num_cond = self.config.data.num_frames_cond
@@ -42,11 +49,23 @@ class BatchedSender:
         n_cycles = 0
         while bool((pos < T).any()):
             n_cycles += 1
-            # conditioning = last num_cond reconstructed frames of every video (finished videos ride along unchanged)
+            # conditioning = last num_cond reconstructed frames of every video
             idx = (pos.clamp(max=T)[:, None] - self.num_cond + torch.arange(self.num_cond, device=dev)[None, :])
             cond = x_ge[ar[:, None], idx].reshape(V, self.num_cond * C, H, W)
-            pred = generate_frame(self.net, cond, config=self.config, sampler=self.sampler, to_host=False,
-                                  max_batch=self.max_batch, **self.sampler_kwargs)  # (V, 5, 3, H, W)
+            active = (pos < T).nonzero().flatten()
+            if self.compact and active.numel() < V:
+                n_act = int(active.numel())
+                n_run = min(V, -(-n_act // self.bucket) * self.bucket)
+                run = torch.cat([active, active[-1:].expand(n_run - n_act)])  # padding repeats the last active video
+                sub = generate_frame(self.net, cond[run], config=self.config, sampler=self.sampler, to_host=False,
+                                     max_batch=self.max_batch, **self.sampler_kwargs)
+                pred = torch.zeros((V,) + tuple(sub.shape[1:]), dtype=sub.dtype, device=dev)
+                pred[active] = sub[:n_act]
+                self.sampled_videos += n_run
+            else:
+                pred = generate_frame(self.net, cond, config=self.config, sampler=self.sampler, to_host=False,
+                                      max_batch=self.max_batch, **self.sampler_kwargs)  # (V, 5, 3, H, W)
+                self.sampled_videos += V
             gidx = (pos[:, None] + torch.arange(self.num_frames, device=dev)[None, :]).clamp(max=x_gt.shape[1] - 1)
             gt = x_gt[ar[:, None], gidx]
             psnr = ops.frame_psnr(pred.contiguous(), gt.contiguous())  # (V, 5) float64

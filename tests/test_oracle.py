@@ -165,3 +165,26 @@ def test_unet_plain(mode):
     n = sum(int(np.prod(s)) for s in shapes.values())
     # ngf=192: 'deep' 80.4 M parameters in 328 tensors (+3 buffers = 331), 'deeper' 240.9 M
     assert (n, len(shapes)) == ((80_434_575, 328) if mode == "deep" else (240_926_991, 390))
+
+
+def test_sender_restatement_invariants():
+    """oracle/sender.py (restatement of city_sender.py:353-437, 519-550) on hand-made cases: accept-all, accept-none and
+    a prefix, with the PSNR of city_sender.py:255-258."""
+    from oracle import sender as RS
+    T, H = 12, 8
+    g = torch.Generator().manual_seed(3)
+    x_gt = torch.rand(T, 3, H, H, generator=g, dtype=torch.float64)
+    perfect = lambda frames: torch.stack([frames[:, 3:6]] * 5, 1)  # repeats the last conditioning frame
+    # threshold -inf: everything accepted, 2 keyframes then 5 per cycle
+    ge, d, n = RS.encode_video(x_gt, perfect, -1e30, total=T)
+    assert d.tolist() == [1, 1] + [0] * 10 and n == 2 and torch.equal(ge[:2], x_gt[:2])
+    # threshold +inf: nothing accepted, all keyframes, one (futile) sampling cycle per pair
+    ge, d, n = RS.encode_video(x_gt, perfect, 1e30, total=T)
+    assert d.tolist() == [1] * T and n == 5 and torch.equal(ge, x_gt)
+    # a video whose frames 2..4 equal frame 1 and then jump: the prefix stops at the jump
+    x2 = x_gt.clone()
+    x2[2:5] = x2[1] + 1e-4
+    ge, d, n = RS.encode_video(x2, perfect, 60.0, total=T)
+    assert d[:7].tolist() == [1, 1, 0, 0, 0, 1, 1]
+    a, b = np.zeros((3, 4, 4)), np.full((3, 4, 4), 0.1)
+    assert abs(RS.cal_psnr(a, b) - 20.0) < 1e-9

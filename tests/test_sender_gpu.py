@@ -55,3 +55,53 @@ def test_batched_sender_cycles():
     assert x_ge.shape == x_gt.shape and set(d.unique().tolist()) <= {0, 1}
     key = d.bool()
     assert torch.equal(x_ge[key], x_gt[key])  # keyframes are the (lossless stand-in) ground truth
+
+
+def _fake_predictor(cond01):
+    """Deterministic stand-in for the diffusion sampler: predicted frame j = the last conditioning frame pulled towards
+    mid-grey by a factor that grows with j and with the frame's first pixel, so that the PSNR against a slowly drifting
+    ground truth falls with j at a video-dependent rate.  A function of the conditioning frames alone: the reference
+    restatement and the batched sender see identical predictions as long as their reconstructions agree."""
+    B, _, H, W = cond01.shape
+    last = cond01[:, 3:6].float()
+    m = last[:, :1, :1, :1]  # a per-video scalar without a reduction: bit-identical for any batch size
+    frames = [(last + (0.5 - last) * (0.015 + 0.08 * m) * (j + 1)).clamp(0, 1) for j in range(5)]
+    return torch.stack(frames, 1)  # (B, 5, 3, H, W)
+
+
+@pytest.mark.parametrize("compact", [False, True])
+def test_batched_sender_equals_reference_loop_per_video(monkeypatch, compact):
+    """BatchedSender against oracle/sender.py (restatement of SenderCity.update / decide_5to5 and the driver's while loop,
+    city_sender.py:353-437, 519-550), video by video: same flags d, same reconstruction x_ge, same number of cycles for the
+    slowest video -- with and without compaction of finished videos."""
+    from evcdiff import sender as S
+    from oracle import sender as RS
+    calls = []
+
+    def fake_generate_frame(net, cond, **kw):
+        calls.append(cond.shape[0])
+        return _fake_predictor(cond)
+    monkeypatch.setattr(S, "generate_frame", fake_generate_frame)
+    g = torch.Generator(device=DEV).manual_seed(7)
+    V, T, H = 11, 30, 32
+    base = torch.rand(V, 1, 3, H, H, device=DEV, generator=g)
+    drift = torch.linspace(0.002, 0.03, V, device=DEV).view(V, 1, 1, 1, 1) * torch.arange(T, device=DEV).view(1, T, 1, 1, 1)
+    x_gt = (base * (0.4 + 0.6 * torch.rand(V, 1, 1, 1, 1, device=DEV, generator=g)) + drift).clamp(0, 1)
+    cfg = common.gpu64_config(device=DEV)
+    thr = 31.0
+    snd = S.BatchedSender(None, cfg, threshold=thr, compact=compact, bucket=4)
+    x_ge, d, n = snd.encode(x_gt)
+    x_ge, d = x_ge.cpu(), d.cpu().numpy()
+    cycles = []
+    for v in range(V):
+        gf = lambda frames: _fake_predictor(frames.to(DEV)).cpu()
+        r_ge, r_d, r_n = RS.encode_video(x_gt[v].cpu(), gf, thr, total=T)
+        assert d[v].tolist() == r_d.tolist(), (v, d[v].tolist(), r_d.tolist())
+        assert torch.equal(x_ge[v], r_ge.float()), v
+        cycles.append(r_n)
+    assert n == max(cycles)
+    assert len(set(cycles)) > 1 and 0 < int(d.sum()) < V * T  # the case really mixes keyframes and predictions
+    if compact:
+        assert snd.sampled_videos < V * n and all(c % 4 == 0 or c == V for c in calls)
+    else:
+        assert snd.sampled_videos == V * n
