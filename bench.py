@@ -200,6 +200,42 @@ def cpu_baseline(n_evals, one_thread=True):
     return out
 
 
+def gpu_eager_context(dev, batch=8, evals=3):
+    """CONTEXT number, not a baseline arm and not the product: the same UNet evaluation as plain
+    PyTorch eager on this GPU (cuDNN / cuBLAS through oracle/ncsnpp.py, the fp32 restatement of the reference modules),
+    in fp32 with TF32 off and under bf16 autocast, `batch` videos, `evals` timed evaluations each, extrapolated to the
+    101 of DDPM-100.  Shows what "the reference's modules moved to the B200 unchanged" would give."""
+    import common
+    from oracle import ncsnpp as O
+    cfg = common.full_config(device=dev)
+    sd = {k: v.to(dev) for k, v in common.seeded_state_dict(O.ncsnpp_param_shapes(cfg), seed=0, active=False).items()}
+    g = torch.Generator(device=dev).manual_seed(1234)
+    x = torch.randn(batch, 15, 128, 128, device=dev, generator=g)
+    cond = torch.rand(batch, 6, 128, 128, device=dev, generator=g) * 2 - 1
+    lab = torch.full((batch,), 500, device=dev, dtype=torch.long)
+    out = {}
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for name, ctx in (("fp32", torch.autocast("cuda", enabled=False)), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+            with torch.no_grad(), ctx:
+                O.ncsnpp_forward(sd, cfg, x, lab, cond)  # untimed: cuDNN algorithm selection
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(evals):
+                    O.ncsnpp_forward(sd, cfg, x, lab, cond)
+                e1.record()
+                torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / evals
+            out[name] = {"frames_per_s": batch * 5.0 / (101 * ms / 1e3), "ms_per_evaluation": ms}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    out["what"] = (f"plain PyTorch eager (cuDNN/cuBLAS) evaluation of the same NCSN++ on this GPU, {batch} videos, {evals} "
+                   "evaluations timed, extrapolated x101; context only (BASELINE.md section 4)")
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -266,6 +302,8 @@ def main():
     ap.add_argument("--cpu-evals", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-launch roofline pass")
+    ap.add_argument("--gpu-eager-context", action="store_true",
+                    help="also time plain PyTorch eager (fp32 and bf16 autocast) on this GPU: context number, N=1 only")
     ap.add_argument("--profile-json", default=None, help="write the per-launch timing table of one evaluation here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -439,6 +477,7 @@ def main():
                         "h2d_bytes_per_step": host_in.numel() * host_in.element_size(),
                         "d2h_bytes_per_step": host_out.numel() * host_out.element_size()},
                 "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu,
+                **({"gpu_eager_context": gpu_eager_context(dev)} if (args.gpu_eager_context and world == 1) else {}),
                 "videos_per_gpu": [pipeline.shard_range(V, r, world)[1] - pipeline.shard_range(V, r, world)[0]
                                    for r in range(world)] if strong else [V] * world,
                 "tflops_per_gpu": value / world * tflop_per_frame}

@@ -93,6 +93,7 @@ struct alignas(64) GemmParams {
   int B, H, W;
   int TW, TH, TB;
   int tiles_x, tiles_y, tiles_b, tiles_n;
+  unsigned mul_tiles_x, mul_tiles_y, mul_tiles_n, mul_split_k;  // fast_div multipliers
   int BN, N;
   int b_batched;
   int num_stages;
@@ -126,15 +127,21 @@ struct alignas(64) GemmParams {
 };
 
 // Work unit `tile` of a CTA (CG = 1) or CTA pair (CG = 2): N tile tn = tile % tiles_n, M tile(s) CG*(tile/tiles_n)+rank.
+// n / d for the tile bookkeeping without the ~25-instruction integer division: m = ceil(2^32 / d) (0: d == 1 or the
+// host could not prove n * d < 2^32, then the plain division is used).  Every warp decodes every tile.
+__device__ __forceinline__ int fast_div(int n, int d, unsigned m) {
+  return m != 0u ? static_cast<int>(__umulhi(static_cast<unsigned>(n), m)) : (d == 1 ? n : n / d);
+}
 template <int CG>
 __device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int rank, int& x0, int& y0, int& b0,
                                             int& n0) {
-  int tn = tile % p.tiles_n;
-  int tm = (tile / p.tiles_n) * CG + rank;  // may be == m_tiles for the peer of the last pair: fully out of range
-  int tx = tm % p.tiles_x;
-  int t2 = tm / p.tiles_x;
-  int ty = t2 % p.tiles_y;
-  int tb = t2 / p.tiles_y;
+  const int tq = fast_div(tile, p.tiles_n, p.mul_tiles_n);
+  int tn = tile - tq * p.tiles_n;
+  int tm = tq * CG + rank;  // may be == m_tiles for the peer of the last pair: fully out of range
+  int t2 = fast_div(tm, p.tiles_x, p.mul_tiles_x);
+  int tx = tm - t2 * p.tiles_x;
+  int tb = fast_div(t2, p.tiles_y, p.mul_tiles_y);
+  int ty = t2 - tb * p.tiles_y;
   x0 = tx * p.TW;
   y0 = ty * p.TH;
   b0 = tb * p.TB;
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     PROF_DECL(long long w_empty = 0;)
     PROF_T0(t_prod);
     for (int u = unit; u < total_units; u += num_units) {
-      const int tile = u / p.split_k;
+      const int tile = fast_div(u, p.split_k, p.mul_split_k);
       const int ks = u - tile * p.split_k;
       const int kb_lo = (ks * p.total_kb) / p.split_k, kb_hi = ((ks + 1) * p.total_kb) / p.split_k;
       int x0, y0, b0, n0;
@@ -579,9 +586,9 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(gn_free_bar(slot_idx));  // this warp is done with the coefficient buffer
     };
-    // the bias vector (tiles_n * BN floats, zero beyond N) is staged once per CTA
+    // the bias vector, pre-multiplied by alpha (tiles_n * BN floats, zero beyond N), is staged once per CTA
     if (p.bias != nullptr)
-      for (int j = e; j < p.tiles_n * p.BN; j += kEpiThreads) sbias_all[j] = (j < p.N) ? __ldg(p.bias + j) : 0.f;
+      for (int j = e; j < p.tiles_n * p.BN; j += kEpiThreads) sbias_all[j] = (j < p.N) ? __ldg(p.bias + j) * p.alpha : 0.f;
     epi_bar();
     int it = 0;
     PROF_DECL(long long w_tfull = 0; long long w_pre = 0; long long w_ld = 0; long long w_rest = 0; long long w_bw = 0;
@@ -590,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     int rit = 0;  // residual tiles fetched by TMA so far (phase of resid_bar)
     volatile int* sk_flag = reinterpret_cast<volatile int*>(tail + 192);  // free bytes of the barrier block
     for (int u = unit; u < total_units; u += num_units, ++it) {
-      const int tile = u / p.split_k;
+      const int tile = fast_div(u, p.split_k, p.mul_split_k);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       int x0, y0, b0, n0;
@@ -827,58 +834,11 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           }
         }
         const int n = n0 + c0;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = (j < ncols) ? __uint_as_float(v[j]) : 0.f;
+        const float al = p.alpha;  // the staged bias is pre-multiplied: out = acc * alpha + bias * alpha + resid * alpha
         if (!SPLIT && p.tma_out != 0) {
-          // ---- staged path (bf16 rows, full 128-row tiles, BN % 32 == 0): +bias +residual, *alpha -> swizzled smem
-          // -> one TMA store per 32 x 32 chunk; rows / columns outside the tensor are clipped by the TMA unit.
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(sbias + c0 + j);
-              f[j + 0] += bv.x;
-              f[j + 1] += bv.y;
-              f[j + 2] += bv.z;
-              f[j + 3] += bv.w;
-            }
-          }
-          if (p.resid_tma) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const int col = c0 + j;
-              const uint4 u = *reinterpret_cast<const uint4*>(sres_t + (col >> 6) * 16384 +
-                                                              ((((col & 63) >> 3) ^ (row & 7)) << 4));
-              f[j + 0] += bf16_lo(u.x);
-              f[j + 1] += bf16_hi(u.x);
-              f[j + 2] += bf16_lo(u.y);
-              f[j + 3] += bf16_hi(u.y);
-              f[j + 4] += bf16_lo(u.z);
-              f[j + 5] += bf16_hi(u.z);
-              f[j + 6] += bf16_lo(u.w);
-              f[j + 7] += bf16_hi(u.w);
-            }
-          } else if (resid_fast) {
-            if (valid) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 u = *reinterpret_cast<const uint4*>(sres + (c0 + j) * 2);
-                f[j + 0] += bf16_lo(u.x);
-                f[j + 1] += bf16_hi(u.x);
-                f[j + 2] += bf16_lo(u.y);
-                f[j + 3] += bf16_hi(u.y);
-                f[j + 4] += bf16_lo(u.z);
-                f[j + 5] += bf16_hi(u.z);
-                f[j + 6] += bf16_lo(u.w);
-                f[j + 7] += bf16_hi(u.w);
-              }
-            }
-          } else if (p.resid != nullptr && valid) {
-            const __nv_bfloat16* r = p.resid + pix * p.resid_ld + n;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n + j < p.N) f[j] += __bfloat162float(r[j]);
-          }
+          // ---- staged path (bf16 rows, full 128-row tiles, BN % 32 == 0): acc * alpha + bias' (+ resid * alpha) ->
+          // swizzled smem -> one TMA store per 32 x 32 chunk; rows / columns outside the tensor are clipped by the TMA
+          // unit.  Eight columns at a time, straight from the TMEM registers.
           const uint32_t boff = (p.tma_out == 2 ? static_cast<uint32_t>(stg_i & 1) : 0u) * 2048u;
           ++stg_i;
           PROF_T0(t_bw);
@@ -891,13 +851,46 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           PROF_T0(t_st);
           uint8_t* srow = stg_base + boff + lane * 64;
           const int sw = (lane >> 1) & 3;
+          const bool has_bias = p.bias != nullptr;
+          const int rmode = p.resid_tma ? 1 : (resid_fast ? (valid ? 2 : 0) : ((p.resid != nullptr && valid) ? 3 : 0));
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
+            float g[8];
+            if (has_bias) {
+              const float4 b0v = *reinterpret_cast<const float4*>(sbias + c0 + 8 * j);
+              const float4 b1v = *reinterpret_cast<const float4*>(sbias + c0 + 8 * j + 4);
+              g[0] = b0v.x; g[1] = b0v.y; g[2] = b0v.z; g[3] = b0v.w;
+              g[4] = b1v.x; g[5] = b1v.y; g[6] = b1v.z; g[7] = b1v.w;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) g[k] = 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = fmaf(__uint_as_float(v[8 * j + k]), al, g[k]);
+            if (rmode == 1 || rmode == 2) {
+              const int col = c0 + 8 * j;
+              const uint4 u = (rmode == 1)
+                  ? *reinterpret_cast<const uint4*>(sres_t + (col >> 6) * 16384 + ((((col & 63) >> 3) ^ (row & 7)) << 4))
+                  : *reinterpret_cast<const uint4*>(sres + col * 2);
+              g[0] = fmaf(bf16_lo(u.x), al, g[0]);
+              g[1] = fmaf(bf16_hi(u.x), al, g[1]);
+              g[2] = fmaf(bf16_lo(u.y), al, g[2]);
+              g[3] = fmaf(bf16_hi(u.y), al, g[3]);
+              g[4] = fmaf(bf16_lo(u.z), al, g[4]);
+              g[5] = fmaf(bf16_hi(u.z), al, g[5]);
+              g[6] = fmaf(bf16_lo(u.w), al, g[6]);
+              g[7] = fmaf(bf16_hi(u.w), al, g[7]);
+            } else if (rmode == 3) {
+              const __nv_bfloat16* r = p.resid + pix * p.resid_ld + n + 8 * j;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (n + 8 * j + k < p.N) g[k] = fmaf(__bfloat162float(r[k]), al, g[k]);
+            }
             uint4 u;
-            u.x = pack_bf16x2(f[8 * j + 0] * p.alpha, f[8 * j + 1] * p.alpha);
-            u.y = pack_bf16x2(f[8 * j + 2] * p.alpha, f[8 * j + 3] * p.alpha);
-            u.z = pack_bf16x2(f[8 * j + 4] * p.alpha, f[8 * j + 5] * p.alpha);
-            u.w = pack_bf16x2(f[8 * j + 6] * p.alpha, f[8 * j + 7] * p.alpha);
+            u.x = pack_bf16x2(g[0], g[1]);
+            u.y = pack_bf16x2(g[2], g[3]);
+            u.z = pack_bf16x2(g[4], g[5]);
+            u.w = pack_bf16x2(g[6], g[7]);
             *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = u;
           }
           fence_proxy_async_smem();
@@ -951,6 +944,9 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
           PROF_ADD(w_rest, t_rest);
           continue;
         }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = (j < ncols) ? __uint_as_float(v[j]) * al : 0.f;
         if (valid) {
           if (p.bias != nullptr) {
 #pragma unroll
@@ -969,30 +965,28 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
             for (int j = 0; j < 32; j += 8) {
               if (j < ncols) {
                 const uint4 u = *reinterpret_cast<const uint4*>(sres + (c0 + j) * 2);
-                f[j + 0] += bf16_lo(u.x);
-                f[j + 1] += bf16_hi(u.x);
-                f[j + 2] += bf16_lo(u.y);
-                f[j + 3] += bf16_hi(u.y);
-                f[j + 4] += bf16_lo(u.z);
-                f[j + 5] += bf16_hi(u.z);
-                f[j + 6] += bf16_lo(u.w);
-                f[j + 7] += bf16_hi(u.w);
+                f[j + 0] = fmaf(bf16_lo(u.x), al, f[j + 0]);
+                f[j + 1] = fmaf(bf16_hi(u.x), al, f[j + 1]);
+                f[j + 2] = fmaf(bf16_lo(u.y), al, f[j + 2]);
+                f[j + 3] = fmaf(bf16_hi(u.y), al, f[j + 3]);
+                f[j + 4] = fmaf(bf16_lo(u.z), al, f[j + 4]);
+                f[j + 5] = fmaf(bf16_hi(u.z), al, f[j + 5]);
+                f[j + 6] = fmaf(bf16_lo(u.w), al, f[j + 6]);
+                f[j + 7] = fmaf(bf16_hi(u.w), al, f[j + 7]);
               }
             }
           } else if (p.resid != nullptr) {
             const __nv_bfloat16* r = p.resid + pix * p.resid_ld + n;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < ncols && n + j < p.N) f[j] += __bfloat162float(r[j]);
+              if (j < ncols && n + j < p.N) f[j] = fmaf(__bfloat162float(r[j]), al, f[j]);
             if (SPLIT && p.resid_lo != nullptr) {
               const __nv_bfloat16* r2 = p.resid_lo + pix * p.resid_ld + n;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < ncols && n + j < p.N) f[j] += __bfloat162float(r2[j]);
+                if (j < ncols && n + j < p.N) f[j] = fmaf(__bfloat162float(r2[j]), al, f[j]);
             }
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
           store_chunk(p, f, ncols, n, pix, b, pin, p.out);
           if (SPLIT && p.out_lo != nullptr) {
             float g[32];
@@ -1058,7 +1052,9 @@ __global__ void __launch_bounds__(kThreads, 1) evc_gemm_kernel(const __grid_cons
     }
     if (!SPLIT && p.gn_fuse && gn_pending) gn_pass2(gn_n0, gn_pix, it - 1);  // `it` = tiles done
     __syncwarp();
-    if (p.tma_out != 0 && elect_one()) bulk_wait_all();  // staging buffers are read before the CTA's smem goes away
+    // the staging buffers must have been read before the CTA's shared memory goes away; the writes themselves complete
+    // with the grid
+    if (p.tma_out != 0 && elect_one()) bulk_wait_read<0>();
 #ifdef EVC_GEMM_PROF
     if (e == 0 && rank == 0) {
       long long tot_epi = 0;
@@ -1452,6 +1448,17 @@ extern "C" int evc_gemm_plan_create(const evc_gemm_desc* d, evc_gemm_plan** out_
   if (cap < 1) cap = 1;
   pl->grid = cg * (int)(units < cap ? units : cap);
   p.sk_coop = (p.split_k > 1 && units <= cap) ? 1 : 0;  // every K slice of every tile on its own resident CTA (pair)
+  {
+    // exact for n * d < 2^32: n <= 2 * units + 1 (unit, tile and M-tile indices), d <= 2^12 here
+    auto mul = [&](int dd) -> unsigned {
+      if (dd <= 1 || (unsigned long long)(2 * units + 4) * (unsigned long long)dd >= (1ull << 32)) return 0u;
+      return (unsigned)(((1ull << 32) + (unsigned long long)dd - 1) / (unsigned long long)dd);
+    };
+    p.mul_tiles_x = mul(p.tiles_x);
+    p.mul_tiles_y = mul(p.tiles_y);
+    p.mul_tiles_n = mul(p.tiles_n);
+    p.mul_split_k = mul(p.split_k);
+  }
   pl->flops = 2.0 * (double)d->B * d->H * d->W * (double)d->w_rows * (double)d->w_k;
   *out_plan = pl;
   return EVC_OK;

@@ -259,6 +259,8 @@ SPLITK_CASES = [
     ("sk_w32_f32rows_s5", 1, 32, 32, [(192, 9)], 384, 1, False, 1.0, 64, 5, 1),
     ("sk_w8_f32T_s7", 1, 8, 8, [(576, 9)], 64, 3, False, 1.0, 32, 7, 1),
     ("sk_uneven_kb_s4", 2, 8, 8, [(192, 9), (64, 1)], 256, 0, False, 1.0, 128, 4, 1),  # 28 K blocks over 4 slices
+    ("sk_w8_n768_s4_serial", 6, 8, 8, [(768, 9)], 768, 0, True, 0.70710678, 96, 6, 1),
+    ("sk_w16_s3_serial", 3, 16, 16, [(384, 9)], 576, 0, False, 1.0, 192, 3, 1),
 ]
 
 
@@ -287,8 +289,11 @@ def test_split_k_gemm(case):
         for rep in range(3):
             out = torch.full(shape, float("nan"), device="cuda", dtype=dt)
             st = torch.zeros(B, N, 2, device="cuda", dtype=torch.int64) if want_stats else None
+            # "_serial" cases cap the grid below the unit count: the K slices of a tile are then not all resident and the
+            # last arriver adds them alone (the cooperative finish needs grid == units)
             plan = ops.GemmPlan(segs, w, out, out_mode, out_ld=ld, out_bs=bs, bias=bias, resid=resid, resid_ld=N, alpha=alpha,
-                                bn=bn, stats=st, cta_group=cg, split_k=split, sk_ws=ws)
+                                bn=bn, stats=st, cta_group=cg, split_k=split, sk_ws=ws,
+                                max_ctas=8 if name.endswith("_serial") else 0)
             assert plan.split_k == split
             plan.launch()
             plan.launch()  # tickets are left at zero by the last arriver: relaunch without any reset
