@@ -1,5 +1,5 @@
 #!/bin/bash
-# One short bench line for each BASELINE.json config that fits one GPU (records for profiles/r01_notes.md).
+# One short bench line for each BASELINE.json config that fits one GPU (records for profiles/rNN_notes.md).
 mkdir -p gpurun_out
 run() { name=$1; shift; python bench.py --steps 1 --warmup 1 --no-cpu-baseline "$@" > gpurun_out/cfg_$name.json 2> gpurun_out/cfg_$name.err; tail -2 gpurun_out/cfg_$name.err
 python - <<PY
@@ -11,7 +11,7 @@ except Exception as e:
     print('$name FAILED', e)
 PY
 }
-run c3_fpndm20_b128 --videos 128 --micro-batch 64 --sampler fpndm --subsample 20
+run c3_fpndm20_b512 --videos 512 --micro-batch 64 --sampler fpndm --subsample 20
 run c4_ddim10 --sampler ddim --subsample 10
 run c4_ddim50 --sampler ddim --subsample 50
 run c5_unet_deep_b32 --model unet_deep --videos 32 --micro-batch 32
