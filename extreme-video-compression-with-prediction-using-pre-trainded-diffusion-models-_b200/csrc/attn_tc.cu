@@ -2,12 +2,15 @@
 // Replaces, per head, the reference's einsum -> softmax -> einsum (models/better/layerspp.py:239-243,
 // models/unet.py:114-119) and round 1's unfused QK^T GEMM + row-softmax + PV GEMM.
 //
-// One CTA per (128-query tile, head, sample).  Two passes over the keys (64 keys per tile):
-//   pass 1:  S = Q K^T            -> running row maximum m            (no exponentials)
-//   pass 2:  S = Q K^T again      -> P = exp2((S - m) * scale*log2 e) (bf16, <= 1), l += row sums, O += P V
-//   end:     O /= l -> bf16
-// Recomputing S (1/3 more MMA work on 1.5 % of the model's FLOPs) removes the online-softmax rescaling of the
-// O accumulator, so O lives untouched in TMEM until the end.
+// One CTA per (128-query tile, head, sample), ONE pass over the keys (64 keys per tile) with an online softmax:
+//   S = Q K^T -> row maximum of the tile; P = exp2((S - m) * scale*log2 e) (bf16), l += row sums, O += P V
+//   end:  O /= l -> bf16
+// The running reference m of a row is only raised when the tile's maximum exceeds it by more than 2^8 (lazy
+// rescaling): P then stays below 2^8 -- harmless for bf16 (relative precision does not depend on magnitude) and for
+// the fp32 accumulators -- and the O accumulator (TMEM) is multiplied by exp2((m_old - m_new) c) by the row's own
+// thread, after the previous P V has completed and before the next one is issued.  With the scores of this model
+// that happens in the first tiles of a row at most (round 1 recomputed S in a second pass instead: 1/3 more MMA work
+// and twice the number of dependent tile hand-offs).
 // Warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = softmax (thread = query row).
 // TMEM: S double buffer 2 x 64 columns at [0,128), O accumulator d columns at [128, 128+d), d <= 384.
 #include "evc_host.h"
@@ -124,8 +127,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_
       __syncwarp();
       if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
     };
-    for (int j = 0; j < T; ++j) load_k(j);  // pass 1
-    load_k(0);                              // pass 2: K_0, then (K_{j+1}, V_j)
+    load_k(0);  // K_0, then (K_{j+1}, V_j)
     for (int j = 0; j < T; ++j) {
       if (j + 1 < T) load_k(j + 1);
       load_v(j);
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_
     const uint32_t idesc_o = umma_idesc_bf16(128u, static_cast<uint32_t>(p.dv_box));
     int stage = 0;
     uint32_t phase = 0;
-    int t = 0;  // S tile counter over both passes: buffer t & 1, phase (t >> 1) & 1
+    int t = 0;  // S tile counter: buffer t & 1, phase (t >> 1) & 1
     auto issue_s = [&]() {
       mbar_wait(kv_full(stage), phase);
       mbar_wait(s_empty(t & 1), ((t >> 1) & 1u) ^ 1u);
@@ -158,8 +160,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_
       ++t;
     };
     mbar_wait(q_full, 0);
-    for (int j = 0; j < T; ++j) issue_s();  // pass 1
-    issue_s();                              // pass 2, S_0
+    issue_s();                              // S_0
     for (int j = 0; j < T; ++j) {
       if (j + 1 < T) issue_s();             // S_{j+1} runs while the softmax warps turn S_j into P_j
       mbar_wait(kv_full(stage), phase);     // V_j
@@ -186,33 +187,44 @@ __global__ void __launch_bounds__(kAttnThreads, 1) evc_attn_kernel(const __grid_
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    float m = -INFINITY;
-    int t = 0;
-    for (int j = 0; j < T; ++j, ++t) {  // pass 1: row maximum
-      mbar_wait(s_full(t & 1), (t >> 1) & 1u);
-      tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32(tmem_S + lane_off + (t & 1) * kBK, v0);
-      tmem_ld_32x32(tmem_S + lane_off + (t & 1) * kBK + 32, v1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty(t & 1));
-#pragma unroll
-      for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
-    }
-    const float mc = m * p.scale_log2e;
+    float mc = -INFINITY;  // running reference of this row, already multiplied by scale * log2(e)
     float l = 0.f;
-    for (int j = 0; j < T; ++j, ++t) {  // pass 2: P = exp2(s*c - m*c)
-      mbar_wait(s_full(t & 1), (t >> 1) & 1u);
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(s_full(j & 1), (j >> 1) & 1u);
       tc_fence_after();
       uint32_t v0[32], v1[32];
-      tmem_ld_32x32(tmem_S + lane_off + (t & 1) * kBK, v0);
-      tmem_ld_32x32(tmem_S + lane_off + (t & 1) * kBK + 32, v1);
+      tmem_ld_32x32(tmem_S + lane_off + (j & 1) * kBK, v0);
+      tmem_ld_32x32(tmem_S + lane_off + (j & 1) * kBK + 32, v1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty(t & 1));
+      if (lane == 0) mbar_arrive(s_empty(j & 1));
+      float mt = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mt = fmaxf(mt, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+      mt *= p.scale_log2e;  // scale > 0
+      // lazy rescaling: keep the old reference unless this tile exceeds it by more than 8 (P would pass 2^8)
+      const bool raise = mt > mc + 8.f;
+      if (__any_sync(0xffffffffu, raise)) {  // warp-uniform: tcgen05.ld / st are warp collectives
+        if (j > 0) {
+          // the previous P V has completed (p_empty of its buffer) and the next one waits for this thread's p_full
+          mbar_wait(p_empty((j - 1) & 1), ((j - 1) >> 1) & 1u);
+          tc_fence_after();
+          const float alpha = raise ? exp2f(mc - mt) : 1.f;  // 0 for the first raise from -inf cannot occur: j > 0
+          l *= alpha;
+          for (int c0 = 0; c0 < d; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32(tmem_O + lane_off + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(tmem_O + lane_off + c0, o);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        if (raise) mc = mt;
+      }
       uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
@@ -339,7 +351,7 @@ extern "C" int evc_attn_plan_create(const evc_attn_desc* a, evc_attn_plan** out)
   p.num_stages = stages;
   pl->smem_bytes = 1024 + q_bytes + stages * st_bytes + p_bytes + 512;
   pl->grid = dim3((a->N + kBQ - 1) / kBQ, a->heads, a->B);
-  pl->flops = 4.0 * a->B * (double)a->N * a->N * a->C;  // QK^T + PV (the recomputed QK^T is not counted)
+  pl->flops = 4.0 * a->B * (double)a->N * a->N * a->C;  // QK^T + PV
   *out = pl;
   return EVC_OK;
 }

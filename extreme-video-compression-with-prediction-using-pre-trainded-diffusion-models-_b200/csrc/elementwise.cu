@@ -296,6 +296,91 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __nv_bfloat16* _
   }
 }
 
+// Streaming form of gn_apply_kernel (bf16 mode): many small blocks instead of one resident wave.  A block covers
+// `pix_per_block` pixels of one sample (16 or 32 per thread in batches of four 16-byte loads, all four in flight before
+// the first is used; no cross-batch prefetch -- the other resident blocks cover the gap) and recomputes the group statistics from the per-channel sums in its prologue (4.5 KB from L2 per
+// ~60 KB of payload); six blocks per SM hide that round trip behind each other's streams.  Same arithmetic as
+// gn_apply_kernel, bit for bit.  Measured against torch's elementwise kernels on the same tensors
+// (tools/gpu_copy_ceiling.py, profiles/r02_notes.md).
+template <bool SILU>
+__global__ void __launch_bounds__(256, 4) gn_apply_stream_kernel(const __nv_bfloat16* __restrict__ x0, int C0,
+                                                              const __nv_bfloat16* __restrict__ x1, int C1, int HW,
+                                                              const long long* __restrict__ stats0,
+                                                              const long long* __restrict__ stats1, int groups, float eps,
+                                                              const float* __restrict__ ss, int adagn,
+                                                              __nv_bfloat16* __restrict__ y, int pix_per_block) {
+  __shared__ float s_mean[64], s_rstd[64];
+  __shared__ float2 s_ch[2048];  // per-channel (sum, sum of squares)
+  pdl_wait();
+  pdl_trigger();
+  const int C = C0 + C1;
+  const int b = blockIdx.y;
+  const int cpg = C / groups;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  const int c = threadIdx.x * 8;
+  const bool first = (c < C0);
+  const int ld = first ? C0 : C1;
+  const int rows = blockDim.y;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(HW, p_begin + pix_per_block);
+  const int p0 = p_begin + threadIdx.y;
+  const __nv_bfloat16* src = (first ? x0 + c : x1 + (c - C0)) + ((long long)b * HW + p0) * ld;
+  __nv_bfloat16* dst = y + ((long long)b * HW + p0) * C + c;
+  const long long sstep = (long long)rows * ld, dstep = (long long)rows * C;
+  // the first batch of pixel loads goes out before the statistics are touched
+  uint4 cur[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (p0 + k * rows < p_end) cur[k] = ld_nc16(src + k * sstep);
+  for (int cc = tid; cc < C; cc += nthr) {
+    const longlong2 st = *reinterpret_cast<const longlong2*>(
+        (cc < C0) ? stats0 + ((long long)b * C0 + cc) * 2 : stats1 + ((long long)b * C1 + (cc - C0)) * 2);
+    s_ch[cc] = make_float2((float)((double)st.x * (1.0 / 1048576.0)), (float)((double)st.y * (1.0 / 1048576.0)));
+  }
+  float gam[8], bet[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(ss + c), g1 = *reinterpret_cast<const float4*>(ss + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(ss + C + c), b1 = *reinterpret_cast<const float4*>(ss + C + c + 4);
+    gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
+    bet[0] = b0.x; bet[1] = b0.y; bet[2] = b0.z; bet[3] = b0.w; bet[4] = b1.x; bet[5] = b1.y; bet[6] = b1.z; bet[7] = b1.w;
+  }
+  __syncthreads();
+  for (int gi = tid; gi < groups; gi += nthr) {  // one thread per group, channels summed in index order (deterministic)
+    float s = 0.f, q = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      const float2 t = s_ch[gi * cpg + j];
+      s += t.x;
+      q += t.y;
+    }
+    const float inv_n = 1.f / ((float)cpg * (float)HW);
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    s_mean[gi] = mean;
+    s_rstd[gi] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  float a[8], bb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    a[j] = s_rstd[g] * (adagn ? (1.f + gam[j]) : gam[j]);
+    bb[j] = bet[j] - s_mean[g] * a[j];
+  }
+  for (int p = p0; p < p_end; p += 4 * rows) {
+    if (p != p0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (p + k * rows < p_end) cur[k] = ld_nc16(src + k * sstep);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (p + k * rows < p_end) *reinterpret_cast<uint4*>(dst + k * dstep) = gn_affine_act<SILU, true>(cur[k], a, bb);
+    src += 4 * sstep;
+    dst += 4 * dstep;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // FIR [1,3,3,1] x2 resampling, separable, zero borders (upfirdn2d modes of upsample_2d / downsample_2d).
 //   up:   out[2i]   = (x[i-1] + 3 x[i]) / 4,  out[2i+1] = (3 x[i] + x[i+1]) / 4      (per axis)
@@ -900,6 +985,32 @@ static int gn_apply_impl(const void* x0, const void* x0_lo, int32_t C0, const vo
     while (ppb > 1 && (long long)((HW + ppb - 2) / (ppb - 1)) * B <= (long long)sms * 3 * waves) --ppb;
   }
   chunks = (HW + ppb - 1) / ppb;
+  static int stream_env = -1;
+  if (stream_env < 0) {
+    const char* e = getenv("EVC_GN_STREAM");
+    stream_env = e ? atoi(e) : 1;
+  }
+  // streaming form for large tensors (same-box sweep, profiles/r02_notes.md): 32 pixels per thread if that still gives
+  // >= 16 blocks per SM, else 16, else the one-wave kernel below (better under ~140 MB).  EVC_GN_STREAM=0 disables it,
+  // EVC_GN_STREAM=n > 1 forces 4n pixels per thread.
+  int sn = 0;
+  if (stream_env > 1) {
+    sn = stream_env;
+  } else if (stream_env == 1) {
+    for (int n = 8; n >= 4 && sn == 0; n >>= 1)
+      if ((long long)B * ((HW + rows * 4 * n - 1) / (rows * 4 * n)) >= 16LL * sms) sn = n;
+  }
+  if (sn > 0 && y_lo == nullptr) {
+    const int sppb = rows * 4 * sn;
+    dim3 sgrid((HW + sppb - 1) / sppb, B), sblock(nvec, rows);
+    cudaError_t se = evc_launch(silu ? gn_apply_stream_kernel<true> : gn_apply_stream_kernel<false>, sgrid, sblock, 0,
+                                (cudaStream_t)stream, 1, reinterpret_cast<const __nv_bfloat16*>(x0), (int)C0,
+                                reinterpret_cast<const __nv_bfloat16*>(x1), (int)C1, (int)HW,
+                                reinterpret_cast<const long long*>(stats0), reinterpret_cast<const long long*>(stats1),
+                                (int)groups, eps, ss, (int)adagn, reinterpret_cast<__nv_bfloat16*>(y), sppb);
+    if (se != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(se));
+    return evc_check_launch("gn_apply_stream_kernel");
+  }
   dim3 grid(chunks, B), block(nvec, rows);
   cudaError_t le = evc_launch(silu ? gn_apply_kernel<true> : gn_apply_kernel<false>, grid, block, 0, (cudaStream_t)stream, 1,
                               reinterpret_cast<const __nv_bfloat16*>(x0), (int)C0, reinterpret_cast<const __nv_bfloat16*>(x1),

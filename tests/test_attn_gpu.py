@@ -34,3 +34,48 @@ def test_fused_attention(B, N, C, heads):
     assert torch.isfinite(out.float()).all()
     err = rel_l2(out.float(), ref)
     assert err < 8e-3, err  # P is rounded to bf16 before the PV product (like the unfused path), output to bf16
+
+
+@pytest.mark.parametrize("B,N,C,heads,mode", [(2, 1024, 384, 2, "ramp"), (1, 512, 256, 1, "ramp"), (2, 256, 192, 1, "late_spike"),
+                                               (1, 1024, 128, 2, "early_spike")])
+def test_fused_attention_online_rescale(B, N, C, heads, mode):
+    """The one-pass online softmax raises a row's reference lazily (only when a key tile exceeds it by more than 2^8) and
+    then rescales the O accumulator in TMEM.  Scores that grow along the key axis force that path in every tile
+    ("ramp"), once near the end ("late_spike") or never after the first tile ("early_spike")."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from evcdiff import ops
+    g = torch.Generator(device="cuda").manual_seed(N + C)
+    d = C // heads
+    scale = d ** -0.5
+    q = torch.randn(B, N, C, device="cuda", generator=g)
+    k = torch.randn(B, N, C, device="cuda", generator=g) * 0.3
+    # add a component along each query's own direction so that q.k grows with the key index
+    qn = q.reshape(B, N, heads, d)
+    u = qn.mean(dim=1, keepdim=True)
+    u = u / u.norm(dim=-1, keepdim=True)  # (B,1,heads,d): one direction per head
+    qn = qn + 6.0 * u  # every query has a positive component along u
+    idx = torch.arange(N, device="cuda", dtype=torch.float32)
+    if mode == "ramp":
+        amp = 40.0 * idx / N  # scores rise by ~ 6 * 40 * scale * log2(e) over the key axis
+    elif mode == "late_spike":
+        amp = torch.where(idx >= N - 40, 30.0, 0.0)
+    else:
+        amp = torch.where(idx < 8, 30.0, 0.0)
+    kn = k.reshape(B, N, heads, d) + amp.view(1, N, 1, 1) * u
+    qk = torch.cat([qn.reshape(B, N, C), kn.reshape(B, N, C)], -1).bfloat16()
+    vT = torch.randn(B, C, N, device="cuda", generator=g).bfloat16()
+    out = torch.full((B, N, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    plan = ops.AttnPlan(qk, vT, out, heads, scale)
+    plan.launch()
+    torch.cuda.synchronize()
+    qf = qk[:, :, :C].float().reshape(B, N, heads, d).permute(0, 2, 1, 3)
+    kf = qk[:, :, C:].float().reshape(B, N, heads, d).permute(0, 2, 1, 3)
+    v = vT.float().reshape(B, heads, d, N).permute(0, 1, 3, 2)
+    s = qf @ kf.transpose(-1, -2) * scale
+    if mode == "ramp":  # the case really spans many rescale thresholds
+        span = (s.max(-1).values - s[..., :64].max(-1).values) * 1.4427
+        assert float(span.median()) > 16.0, float(span.median())  # at least two raises of the reference per row
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B, N, C)
+    assert torch.isfinite(out.float()).all()
+    err = rel_l2(out.float(), ref)
+    assert err < 8e-3, err
