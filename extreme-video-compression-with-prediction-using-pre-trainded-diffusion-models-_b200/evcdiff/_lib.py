@@ -39,7 +39,7 @@ class GemmDesc(C.Structure):
 class AttnDesc(C.Structure):
     _fields_ = [("qk", C.c_void_p), ("qk_ld", C.c_int64), ("vT", C.c_void_p), ("vT_ld", C.c_int64),
                 ("out", C.c_void_p), ("out_ld", C.c_int64), ("B", C.c_int32), ("N", C.c_int32), ("C", C.c_int32),
-                ("heads", C.c_int32), ("scale", C.c_float)]
+                ("heads", C.c_int32), ("scale", C.c_float), ("v", C.c_void_p), ("v_ld", C.c_int64)]
 
 
 class StepCoef(C.Structure):

@@ -128,6 +128,7 @@ class EngineBase:
         self._deferred = []
         self.fixed_groups = None  # models/unet.py: always 32 groups; NCSN++: min(C//4, 32)
         self.fused_attention = os.environ.get("EVC_FUSED_ATTENTION", "1") != "0"
+        self.fused_qkv = os.environ.get("EVC_FUSED_QKV", "1") != "0"  # one q|k|v projection, V rows as an MN-major operand
         self.ws_bytes = 256
         # split-K partial tiles (fp32) of the launches with few M tiles; one buffer, the launches are stream-ordered
         self.sk_ws = None if self.split else torch.empty(ops.SPLIT_K_WS_BYTES, dtype=torch.uint8, device=self.device)
@@ -310,9 +311,9 @@ class EngineBase:
     def attn_core(self, x, ss, gn_eps, ws, bs, heads, out_alpha):
         """out = out_alpha * (x + OUT(softmax(q k^T / sqrt(d)) v)) with q,k,v = 1x1 projections of GN(x).
         ws/bs: [Wq, Wk, Wv, Wo] as (out, in) fp32 and fp32 biases.  The softmax(QK^T)V core is the fused tcgen05
-        attention kernel (evc_attn_*) when N % 64 == 0 and the head dim is a multiple of 64 (<= 384); otherwise (and
-        always in split-precision mode) batched GEMMs with a per-sample B operand (K, then V^T from a transposed-store
-        epilogue) + row softmax."""
+        attention kernel (evc_attn_*) behind ONE q|k|v projection when N % 64 == 0 and the head dim is a multiple of 64
+        (ops.attn_supported); otherwise (and always in split-precision mode) batched GEMMs with a per-sample B operand
+        (K, then V^T from a transposed-store epilogue) + row softmax."""
         dev = self.device
         C, N, B = x.C, x.H * x.W, self.B
         d = C // heads
@@ -324,6 +325,33 @@ class EngineBase:
         hn = self.new_act(x.H, x.W, C)
         self.gn_apply(x, None, lambda li: ss, gn_eps, False, False, hn)
         sp = self.split
+        fused = self.fused_attention and not sp and ops.attn_supported(N, C, heads)
+        if fused:
+            # one q|k|v projection; the attention kernel reads V rows as an MN-major operand (no transposed V^T store)
+            vT = None
+            if self.fused_qkv:
+                qkv = self.pool.get((B, x.H, x.W, 3 * C))
+                self.gemm([(hn, 1)], torch.cat([wq, wk, wv], 0).contiguous(), qkv, EVC_OUT_BF16_ROWS, 3 * C,
+                          bias=torch.cat([bq, bk, bv]).contiguous())
+            else:  # A/B (EVC_FUSED_QKV=0): round-2a layout, q|k rows + V^T from a transposed-store projection
+                qkv = self.pool.get((B, x.H, x.W, 2 * C))
+                vT = self.pool.get((B, C, N))
+                self.gemm([(hn, 1)], torch.cat([wq, wk], 0).contiguous(), qkv, EVC_OUT_BF16_ROWS, 2 * C,
+                          bias=torch.cat([bq, bk]).contiguous())
+                self.gemm([(hn, 1)], wv, vT, EVC_OUT_BF16_T, N, out_bs=C * N, bias=bv)
+            o = self.new_act(x.H, x.W, C)
+            qkv3 = qkv.view(B, N, qkv.shape[-1])
+            plan = ops.AttnPlan(qkv3, vT, o.t.view(B, N, C), heads, float(int(d) ** (-0.5)),
+                                v=qkv3[:, :, 2 * C:] if vT is None else None)
+            self.flops += plan.flops
+            self._op(lambda li, plan=plan: plan.launch(), "attn", dict(flops=plan.flops, N=N, d=d, heads=heads))
+            out = self.new_act(x.H, x.W, C, scratch=False)
+            self.gemm([(o, 1)], wo, out.t, EVC_OUT_BF16_ROWS, C, bias=bo, resid=x, alpha=out_alpha, stats_of=out)
+            self.pool.put(qkv)
+            if vT is not None:
+                self.pool.put(vT)
+            self.release(hn, o)
+            return out
         qk = self.pool.get((B, x.H, x.W, 2 * C))
         qk_lo = self.pool.get((B, x.H, x.W, 2 * C)) if sp else None
         self.gemm([(hn, 1)], torch.cat([wq, wk], 0).contiguous(), qk, EVC_OUT_BF16_ROWS, 2 * C,
@@ -331,11 +359,8 @@ class EngineBase:
         # key axis padded to a multiple of 8 (16-byte TMA strides); only toy shapes (N < 8) ever pad.  Pad columns:
         # S = -inf (never written by the GEMM, so softmax gives P = 0) and V^T = 0.
         Np = max(8, (N + 7) // 8 * 8)
-        fused = self.fused_attention and not sp and ops.attn_supported(N, C, heads)
         S = Pm = Pm_lo = vT_lo = None
-        if fused:
-            vT = self.pool.get((B, C, N))
-        elif Np == N:
+        if Np == N:
             vT = self.pool.get((B, C, N))
             S = self.pool.get((B, N, N), torch.float32)
             Pm = self.pool.get((B, N, N))
@@ -353,30 +378,25 @@ class EngineBase:
         o = self.new_act(x.H, x.W, C)
         qk3 = qk.view(B, N, 2 * C)
         o3 = o.t.view(B, N, C)
-        if fused:
-            plan = ops.AttnPlan(qk3, vT, o3, heads, float(int(d) ** (-0.5)))
-            self.flops += plan.flops
-            self._op(lambda li, plan=plan: plan.launch(), "attn", dict(flops=plan.flops, N=N, d=d, heads=heads))
-        else:
-            qk3_lo = qk_lo.view(B, N, 2 * C) if sp else None
-            o3_lo = o.lo.view(B, N, C) if sp else None
-            for hd in range(heads):
-                q = qk3[:, :, hd * d:(hd + 1) * d].unsqueeze(1)  # (B,1,N,d)
-                k = qk3[:, :, C + hd * d:C + (hd + 1) * d]  # (B,N,d)  per-sample B operand
-                q_lo = [qk3_lo[:, :, hd * d:(hd + 1) * d].unsqueeze(1)] if sp else None
-                k_lo = qk3_lo[:, :, C + hd * d:C + (hd + 1) * d] if sp else None
-                self.gemm([(q, 1)], k, S, EVC_OUT_F32_ROWS, Np, alpha=float(int(d) ** (-0.5)), w_lo=k_lo, segs_lo=q_lo)
-                self._op(lambda li, S=S, Pm=Pm, Pl=Pm_lo: ops.softmax_rows(S, Pm, B * N, Np, P_lo=Pl), "softmax",
-                         dict(bytes=B * N * Np * 6))
-                self.gemm([(Pm.view(B, 1, N, Np), 1)], vT[:, hd * d:(hd + 1) * d, :], o3[:, :, hd * d:],
-                          EVC_OUT_BF16_ROWS, C, w_lo=vT_lo[:, hd * d:(hd + 1) * d, :] if sp else None,
-                          segs_lo=[Pm_lo.view(B, 1, N, Np)] if sp else None, out_lo=o3_lo[:, :, hd * d:] if sp else None)
+        qk3_lo = qk_lo.view(B, N, 2 * C) if sp else None
+        o3_lo = o.lo.view(B, N, C) if sp else None
+        for hd in range(heads):
+            q = qk3[:, :, hd * d:(hd + 1) * d].unsqueeze(1)  # (B,1,N,d)
+            k = qk3[:, :, C + hd * d:C + (hd + 1) * d]  # (B,N,d)  per-sample B operand
+            q_lo = [qk3_lo[:, :, hd * d:(hd + 1) * d].unsqueeze(1)] if sp else None
+            k_lo = qk3_lo[:, :, C + hd * d:C + (hd + 1) * d] if sp else None
+            self.gemm([(q, 1)], k, S, EVC_OUT_F32_ROWS, Np, alpha=float(int(d) ** (-0.5)), w_lo=k_lo, segs_lo=q_lo)
+            self._op(lambda li, S=S, Pm=Pm, Pl=Pm_lo: ops.softmax_rows(S, Pm, B * N, Np, P_lo=Pl), "softmax",
+                     dict(bytes=B * N * Np * 6))
+            self.gemm([(Pm.view(B, 1, N, Np), 1)], vT[:, hd * d:(hd + 1) * d, :], o3[:, :, hd * d:],
+                      EVC_OUT_BF16_ROWS, C, w_lo=vT_lo[:, hd * d:(hd + 1) * d, :] if sp else None,
+                      segs_lo=[Pm_lo.view(B, 1, N, Np)] if sp else None, out_lo=o3_lo[:, :, hd * d:] if sp else None)
         out = self.new_act(x.H, x.W, C, scratch=False)
         self.gemm([(o, 1)], wo, out.t, EVC_OUT_BF16_ROWS, C, bias=bo, resid=x, alpha=out_alpha, stats_of=out)
         self.pool.put(qk)
         if sp:
             self.pool.put(qk_lo)
-        if fused or Np == N:
+        if Np == N:
             for t in (vT, S, Pm, vT_lo, Pm_lo):
                 if t is not None:
                     self.pool.put(t)

@@ -147,24 +147,37 @@ class GemmPlan:
 
 def attn_supported(N, C, heads):
     d = C // heads
-    return N % 64 == 0 and d % 64 == 0 and d <= 384 and (d <= 256 or d % 128 == 0)
+    if N % 64 or d % 64:
+        return False
+    if d <= 384:
+        return d <= 256 or d % 128 == 0
+    # larger heads: output columns split over CTAs in slices of <= 256 columns (multiples of 64)
+    return any(d % s == 0 and (d // s) % 64 == 0 and d // s <= 256 for s in range(2, 17))
 
 
 class AttnPlan:
-    """Fused attention launch: out (B,N,C) = softmax(scale q k^T) v per head, from qk (B,N,2C) and vT (B,C,N)."""
+    """Fused attention launch: out (B,N,C) = softmax(scale q k^T) v per head, from qk (B,N,>=2C) and either vT (B,C,N)
+    or, with vT=None, v (B,N,C) rows (a strided view, e.g. the last C columns of a fused q|k|v projection)."""
 
-    def __init__(self, qk, vT, out, heads, scale):
+    def __init__(self, qk, vT, out, heads, scale, v=None):
         lib = load()
-        _require_cuda(qk, vT, out)
         B, N, C2 = qk.shape
-        Cc = C2 // 2
-        assert vT.shape == (B, Cc, N) and out.shape[:2] == (B, N) and qk.stride(2) == 1 and vT.stride(2) == 1
         d = AttnDesc()
+        if vT is not None:
+            _require_cuda(qk, vT, out)
+            Cc = C2 // 2
+            assert vT.shape == (B, Cc, N) and vT.stride(2) == 1
+            d.vT, d.vT_ld = vT.data_ptr(), vT.stride(1)
+        else:
+            _require_cuda(qk, v, out)
+            Cc = v.shape[2]
+            assert v.shape == (B, N, Cc) and v.stride(2) == 1 and v.stride(0) == N * v.stride(1) and C2 >= 2 * Cc
+            d.v, d.v_ld = v.data_ptr(), v.stride(1)
+        assert out.shape[:2] == (B, N) and qk.stride(2) == 1 and qk.stride(0) == N * qk.stride(1)
         d.qk, d.qk_ld = qk.data_ptr(), qk.stride(1)
-        d.vT, d.vT_ld = vT.data_ptr(), vT.stride(1)
         d.out, d.out_ld = out.data_ptr(), out.stride(1)
         d.B, d.N, d.C, d.heads, d.scale = B, N, Cc, heads, scale
-        self._keep = (qk, vT, out)
+        self._keep = (qk, vT, v, out)
         self._lib = lib
         h = C.c_void_p()
         check(lib.evc_attn_plan_create(C.byref(d), C.byref(h)), "evc_attn_plan_create")

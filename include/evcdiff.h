@@ -168,9 +168,12 @@ int evc_gemm_plan_cta_group(const evc_gemm_plan* plan);
  * Fused self-attention forward (flash-style, tcgen05): out[b, q, h*d + :] = softmax(scale * Q_h K_h^T) V_h with
  *   Q_h = qk[b, q, h*d : (h+1)*d],  K_h = qk[b, k, C + h*d : C + (h+1)*d]   (qk: (B, N, >= 2C) bf16 rows, row stride qk_ld)
  *   V_h^T = vT[b, h*d : (h+1)*d, k]                                          (vT: (B, C, N) bf16, row stride vT_ld)
+ *   or, with vT == NULL,  V_h = v[b, k, h*d : (h+1)*d]                       (v: (B, N, >= C) bf16 rows, row stride v_ld;
+ *                                                                             e.g. columns 2C.. of one fused q|k|v projection)
  * Replaces einsum -> softmax -> einsum of AttnBlockpp / AttnBlock (layerspp.py:239-243, unet.py:114-119); the N x N
- * score matrix never leaves the SM.  Needs N % 64 == 0, d = C/heads % 64 == 0, d <= 384 (EVC_ERR_UNSUPPORTED
- * otherwise: the caller then uses the batched-GEMM + evc_softmax_rows formulation).
+ * score matrix never leaves the SM.  Needs N % 64 == 0, d = C/heads % 64 == 0 (% 128 for 256 < d <= 384); head dims
+ * above 384 (unet.py 'deeper': one head of 768) split the output columns of a head over several CTAs
+ * (EVC_ERR_UNSUPPORTED otherwise: the caller then uses the batched-GEMM + evc_softmax_rows formulation).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct evc_attn_desc {
   const void* qk;
@@ -181,6 +184,8 @@ typedef struct evc_attn_desc {
   int64_t out_ld;
   int32_t B, N, C, heads;
   float scale;
+  const void* v;   /* used when vT == NULL */
+  int64_t v_ld;
 } evc_attn_desc;
 typedef struct evc_attn_plan evc_attn_plan;
 int evc_attn_plan_create(const evc_attn_desc* desc, evc_attn_plan** plan);
