@@ -755,6 +755,179 @@ __global__ void __launch_bounds__(256, (V == 8) ? 2 : 3) gn_fir_kernel(const GnF
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Down-sampling form of the fused prologue with every input element loaded and activated exactly ONCE (the walk above
+// activates it twice: neighbouring output columns share two of their four input columns, and SiLU costs 1.5 MUFU ops).
+// A thread owns 8 channels of one INPUT column and walks down the rows: the vertical half of the separable filter runs
+// in registers (carry = .125 r[2oy-1] + .375 r[2oy] from the previous step, this step adds .375 r[2oy+1] + .125 r[2oy+2]),
+// the horizontal half exchanges the vertically reduced rows (raw and activated, fp32) through a double-buffered
+// shared-memory row: one __syncthreads per output row, and all threads share the 2 * OXB * nvb output vectors.
+// block = (nvb channel vectors, NC = 2*OXB + 2 input columns incl. the halo); grid = (column blocks * channel chunks,
+// row strips, B); dynamic shared memory 2 buffers x 2 planes x NC x (nvb * 8) floats.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(416, 2) gn_fir_down_kernel(const GnFirArgs g, int OXB, int CB, int n_chunks) {
+  extern __shared__ float s_x[];
+  __shared__ float s_mean[64], s_rstd[64];
+  __shared__ float2 s_ch[2048];
+  pdl_wait();
+  pdl_trigger();
+  const int C = g.C0 + g.C1, H = g.H, W = g.W, OH = H / 2, OW = W / 2;
+  const int b = blockIdx.z;
+  const int cpg = C / g.groups;
+  const int nvb = blockDim.x, NC = blockDim.y;
+  const int vx = threadIdx.x, cx = threadIdx.y;
+  const int tid = cx * nvb + vx, nthr = nvb * NC;
+  const int chunk = blockIdx.x % n_chunks, xblk = blockIdx.x / n_chunks;
+  const int c = chunk * CB + vx * 8;  // first channel of this thread
+  // ---- GroupNorm coefficients (same arithmetic as gn_apply_kernel / gn_fir_kernel)
+  for (int cc = tid; cc < C; cc += nthr) {
+    const longlong2 st = *reinterpret_cast<const longlong2*>(
+        (cc < g.C0) ? g.stats0 + ((long long)b * g.C0 + cc) * 2 : g.stats1 + ((long long)b * g.C1 + (cc - g.C0)) * 2);
+    s_ch[cc] = make_float2((float)((double)st.x * (1.0 / 1048576.0)), (float)((double)st.y * (1.0 / 1048576.0)));
+  }
+  float a[8], bb[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(g.ss + c), g1 = *reinterpret_cast<const float4*>(g.ss + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(g.ss + C + c), b1 = *reinterpret_cast<const float4*>(g.ss + C + c + 4);
+    a[0] = g0.x; a[1] = g0.y; a[2] = g0.z; a[3] = g0.w; a[4] = g1.x; a[5] = g1.y; a[6] = g1.z; a[7] = g1.w;
+    bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+  }
+  __syncthreads();
+  for (int gi = tid; gi < g.groups; gi += nthr) {
+    float sm = 0.f, q = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      const float2 t = s_ch[gi * cpg + j];
+      sm += t.x;
+      q += t.y;
+    }
+    const float inv_n = 1.f / ((float)cpg * (float)(H * W));
+    const float mean = sm * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    s_mean[gi] = mean;
+    s_rstd[gi] = rsqrtf(var + g.eps);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int gi = (c + j) / cpg;
+    const float gam = s_rstd[gi] * (g.adagn ? (1.f + a[j]) : a[j]);
+    bb[j] = bb[j] - s_mean[gi] * gam;
+    a[j] = gam;
+  }
+  const bool first = (c < g.C0);
+  const int Cs = first ? g.C0 : g.C1;
+  const int cs = first ? c : c - g.C0;
+  const int ox0 = xblk * OXB;
+  const int gx = 2 * ox0 - 1 + cx;  // this thread's input column
+  const bool col_ok = (gx >= 0) && (gx < W);
+  const __nv_bfloat16* xs = (first ? g.x0 : g.x1) + ((long long)b * H * W + (col_ok ? gx : 0)) * Cs + cs;
+  const int o0 = blockIdx.y * g.strip, o1 = min(OH, o0 + g.strip);
+  const int pitch = nvb * 8;                 // floats per column
+  const int plane = NC * pitch;              // floats per (raw | act) plane
+  auto load_row = [&](int r) -> uint4 {
+    if (!col_ok || r < 0 || r >= H) return make_uint4(0u, 0u, 0u, 0u);
+    return ld_nc16(xs + (long long)r * W * Cs);
+  };
+  // rows outside the image contribute zeros to BOTH outputs (upfirdn2d pads the activated tensor, layerspp.py:604-611)
+  auto row_ok = [&](int r) { return col_ok && r >= 0 && r < H; };
+  float cr[8], ca[8];  // carry: .125 r[2oy-1] + .375 r[2oy], raw and activated
+  {
+    const uint4 u0 = load_row(2 * o0 - 1), u1 = load_row(2 * o0);
+    float r0[8], r1[8], a0[8], a1[8];
+    unpack8(u0, r0);
+    unpack8(u1, r1);
+    const bool k0 = row_ok(2 * o0 - 1), k1 = row_ok(2 * o0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a0[j] = fmaf(r0[j], a[j], bb[j]);
+      a1[j] = fmaf(r1[j], a[j], bb[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      silu_pair(a0[j], a0[j + 1]);
+      silu_pair(a1[j], a1[j + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      cr[j] = 0.125f * r0[j] + 0.375f * r1[j];
+      ca[j] = (k0 ? 0.125f * a0[j] : 0.f) + (k1 ? 0.375f * a1[j] : 0.f);
+    }
+  }
+  // phase-2 role of this thread: output vector (which plane, output column, channel vector)
+  const int items = 2 * OXB * nvb;
+  const bool p2 = tid < items;
+  const int which = tid / (OXB * nvb);
+  const int rem = tid - which * (OXB * nvb);
+  const int p2ox = rem / nvb, p2vx = rem - p2ox * nvb;
+  const int p2c = chunk * CB + p2vx * 8;
+  const bool p2first = p2c < g.C0;
+  __nv_bfloat16* p2dst;
+  long long p2ld;
+  if (which == 0) {  // raw (skip path): FIR(x0) / FIR(x1) as separate tensors
+    const int Cd = p2first ? g.C0 : g.C1;
+    p2dst = (p2first ? g.y_raw0 : g.y_raw1) + (long long)b * OH * OW * Cd + (p2first ? p2c : p2c - g.C0);
+    p2ld = Cd;
+  } else {
+    p2dst = g.y_act + (long long)b * OH * OW * C + p2c;
+    p2ld = C;
+  }
+  const bool p2ok = p2 && (ox0 + p2ox) < OW;
+  uint4 n0 = load_row(2 * o0 + 1), n1 = load_row(2 * o0 + 2);
+  int buf = 0;
+  for (int oy = o0; oy < o1; ++oy) {
+    float r0[8], r1[8], a0[8], a1[8];
+    unpack8(n0, r0);
+    unpack8(n1, r1);
+    const bool k0 = row_ok(2 * oy + 1), k1 = row_ok(2 * oy + 2);
+    if (oy + 1 < o1) {  // next step's rows are in flight while this one is reduced and exchanged
+      n0 = load_row(2 * oy + 3);
+      n1 = load_row(2 * oy + 4);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a0[j] = fmaf(r0[j], a[j], bb[j]);
+      a1[j] = fmaf(r1[j], a[j], bb[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      silu_pair(a0[j], a0[j + 1]);
+      silu_pair(a1[j], a1[j + 1]);
+    }
+    float vr[8], va[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x0 = k0 ? a0[j] : 0.f, x1 = k1 ? a1[j] : 0.f;
+      vr[j] = cr[j] + 0.375f * r0[j] + 0.125f * r1[j];
+      va[j] = ca[j] + 0.375f * x0 + 0.125f * x1;
+      cr[j] = 0.125f * r0[j] + 0.375f * r1[j];
+      ca[j] = 0.125f * x0 + 0.375f * x1;
+    }
+    // column cx, two float4 planes per 8-channel vector (conflict-free 16-byte accesses along vx)
+    float* sb = s_x + buf * 2 * plane + cx * pitch + vx * 4;
+    *reinterpret_cast<float4*>(sb) = make_float4(vr[0], vr[1], vr[2], vr[3]);
+    *reinterpret_cast<float4*>(sb + nvb * 4) = make_float4(vr[4], vr[5], vr[6], vr[7]);
+    *reinterpret_cast<float4*>(sb + plane) = make_float4(va[0], va[1], va[2], va[3]);
+    *reinterpret_cast<float4*>(sb + plane + nvb * 4) = make_float4(va[4], va[5], va[6], va[7]);
+    __syncthreads();
+    if (p2ok) {
+      const float* sp = s_x + buf * 2 * plane + which * plane + (2 * p2ox) * pitch + p2vx * 4;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float w = (t == 0 || t == 3) ? 0.125f : 0.375f;
+        const float4 lo = *reinterpret_cast<const float4*>(sp + t * pitch);
+        const float4 hi = *reinterpret_cast<const float4*>(sp + t * pitch + nvb * 4);
+        o[0] = fmaf(w, lo.x, o[0]); o[1] = fmaf(w, lo.y, o[1]); o[2] = fmaf(w, lo.z, o[2]); o[3] = fmaf(w, lo.w, o[3]);
+        o[4] = fmaf(w, hi.x, o[4]); o[5] = fmaf(w, hi.y, o[5]); o[6] = fmaf(w, hi.z, o[6]); o[7] = fmaf(w, hi.w, o[7]);
+      }
+      *reinterpret_cast<uint4*>(p2dst + ((long long)oy * OW + ox0 + p2ox) * p2ld) = pack8(o);
+    }
+    buf ^= 1;
+  }
+}
+
 __global__ void nearest_up2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H,
                                    int W, int C) {
   const int nvec = C / 8;
@@ -1045,6 +1218,39 @@ extern "C" int evc_gn_fir(const void* x0, int32_t C0, const void* x1, int32_t C1
   g.y_act = reinterpret_cast<__nv_bfloat16*>(y_act);
   g.y_raw0 = reinterpret_cast<__nv_bfloat16*>(y_raw0);
   g.y_raw1 = reinterpret_cast<__nv_bfloat16*>(y_raw1);
+  static int down_env = -1;
+  if (down_env < 0) {
+    const char* e = getenv("EVC_GN_FIR_DOWN");  // 0: the two-activations-per-input walk (A/B)
+    down_env = e ? atoi(e) : 1;
+  }
+  if (!up && down_env) {
+    // channel chunk per block: the largest multiple of 8 that divides C and is <= 96
+    int CB = 8;
+    for (int cb = 96; cb >= 8; cb -= 8)
+      if (C % cb == 0) { CB = cb; break; }
+    const int nvb = CB / 8, n_chunks = C / CB;
+    const int OW = W / 2, OH = H / 2;
+    int OXB = (416 / nvb - 2) / 2;
+    if (OXB > OW) OXB = OW;
+    if (OXB < 1) OXB = 1;
+    const int NC = 2 * OXB + 2;
+    const int xb = (OW + OXB - 1) / OXB;
+    int strip = 16;
+    while (strip > 4 && (long long)xb * n_chunks * ((OH + strip - 1) / strip) * B < 2ll * evc_num_sms()) strip >>= 1;
+    if (strip > OH) strip = OH;
+    g.strip = strip;
+    const size_t smem = (size_t)2 * 2 * NC * CB * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t ae = cudaFuncSetAttribute(gn_fir_down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      if (ae != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(ae));
+      attr_set = true;
+    }
+    dim3 grid(xb * n_chunks, (OH + strip - 1) / strip, B), block(nvb, NC);
+    cudaError_t le = evc_launch(gn_fir_down_kernel, grid, block, smem, (cudaStream_t)stream, 1, g, OXB, CB, n_chunks);
+    if (le != cudaSuccess) return evc_set_error(EVC_ERR_CUDA, cudaGetErrorString(le));
+    return evc_check_launch("gn_fir_down_kernel");
+  }
   // 4 channels per thread (twice the resident warps) wherever the channel count allows a <= 256-wide block row
   static int vec_env = -1;
   if (vec_env < 0) {

@@ -80,6 +80,7 @@ def test_fir(B, H, C):
     (2, 16, 192, 0, True), (2, 16, 192, 0, False), (3, 8, 768, 576, True), (2, 32, 384, 192, True),
     (2, 32, 384, 192, False), (1, 64, 192, 0, False), (1, 64, 192, 192, True), (2, 4, 64, 32, True), (2, 4, 64, 32, False),
     (1, 34, 192, 0, False), (1, 20, 64, 0, True), (2, 2, 96, 0, False), (2, 1, 128, 96, True), (2, 2, 96, 64, True),
+    (1, 128, 192, 0, False), (2, 16, 576, 0, False), (1, 12, 24, 8, False), (3, 6, 40, 0, False), (1, 70, 64, 0, False),
 ])
 def test_gn_fir_fused(B, H, C0, C1, up):
     """FIR(SiLU(AdaGN([x0|x1]))) and FIR(x) from one kernel (up / down res-block prologue, layerspp.py:598-611)."""

@@ -3,7 +3,8 @@ vectors (generated from the unmodified reference).
 
 Tolerances (north_star, bf16 compute mode): per-step x_t rel-L2 <= 1e-2; final-frame PSNR within 0.05 dB of the
 fp32 result.  eps of a single evaluation is compared directly as well (SURVEY.md section 4 trap: at default
-init x_t is insensitive to the UNet), bound 3e-2 (the reference under bf16 autocast measures 1.9e-2, section 4a).
+init x_t is insensitive to the UNet), bound 1.5e-2 (measured 0.7-1.3e-2; the reference itself under bf16 autocast
+measures 1.9e-2, section 4a).
 """
 import os
 
@@ -18,7 +19,7 @@ from oracle import samplers as S
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-EPS_TOL = 3e-2
+EPS_TOL = 1.5e-2
 XT_TOL = 1e-2
 
 
@@ -191,7 +192,7 @@ def test_teacher_forced_steps_and_graph_equals_eager():
     torch.cuda.manual_seed_all(1234)
     c = M.ddpm_sampler(x_T.clone(), net, cond=cond, final_only=True, subsample_steps=20, graph=True)  # replay
     assert torch.equal(b, c)
-    assert common.rel_l2(a, b) < 1e-3  # atomics in the GroupNorm reduction are order-nondeterministic
+    assert torch.equal(a, b)  # eager launches == captured graph, bit for bit (fixed-point integer atomics, fixed split-K order)
     # the same generator draws as the reference loop: randn_like per step after seeding
     torch.manual_seed(1234)
     torch.cuda.manual_seed_all(1234)
