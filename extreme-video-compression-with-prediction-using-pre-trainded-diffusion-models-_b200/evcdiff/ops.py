@@ -204,6 +204,28 @@ def m_tiles(B, H, W, batched):
     return (W // tw) * (H // th) * (-(-B // tb))
 
 
+def _pairs(mt, bn):
+    """CTA pairs?  (mirrors evc_gemm_plan_create)"""
+    return mt >= 8 and (mt % 2 == 0 or mt >= 23) and bn % 16 == 0
+
+
+def kblock_cycles(bn, cg):
+    """SM cycles per 64-wide K block of one 128-row tile: four tcgen05.mma (N/2 cycles each, ~48 at least:
+    profiles/r02_umma_microbench.jsonl) or the delivery of 128 A rows + this CTA's share of the B rows by the TMA unit,
+    whichever is longer.  Measured (profiles/r02_bn_probe.txt, 6 videos): 389 / ~285 / ~280 cycles for N tiles of 192 / 96 /
+    64 in CTA pairs -- a narrower N tile re-reads the A tile, so it is never much cheaper per tile."""
+    row = 1.74 if cg == 2 else TMA_CYCLES_PER_ROW
+    return max(4 * max(bn // 2, 48), row * (128 + bn / cg))
+
+
+def unsplit_cost(n, mt, kblocks, bn, sms):
+    tiles = mt * (n // bn)
+    waves = -(-tiles // sms)
+    epi = 1500 + 12 * bn  # drains behind the next tile's main loop (two accumulator stages) unless the K loop is shorter
+    per_tile = max(kblocks * kblock_cycles(bn, 2 if _pairs(mt, bn) else 1), epi)
+    return waves * per_tile + epi
+
+
 def pick_bn(n, mt=None, kblocks=None, sms=148):
     """N tile of the 128-row UMMA.  Large problems: the widest tile that divides N (fewest A re-reads, best
     MMA efficiency).  Problems with few M tiles (8x8 / 16x16 levels, small batches): the tile that minimises
@@ -213,13 +235,17 @@ def pick_bn(n, mt=None, kblocks=None, sms=148):
         return min(256, ((n + 15) // 16) * 16)
     if mt is None or kblocks is None:
         return cands[0]
+    # more tiles than SMs even with the widest N tile: several rounds of the persistent grid, where a narrower tile pays
+    # the A re-read in every round (unsplit_cost); otherwise the fill-the-SMs model below.  EVC_PICK_MODEL=old: A/B
+    old = os.environ.get("EVC_PICK_MODEL", "new") == "old" or mt * (n // cands[0]) <= sms
     best, best_cost = None, None
     for bn in cands:
-        tiles = mt * (n // bn)
-        waves = -(-tiles // sms)
-        # cycles: 4 MMAs of bn/2 cycles per 64-wide K block (min 32 each), + pipeline fill + epilogue.  (The measured
-        # cost of a 128-row UMMA is max(154, bn/2 + 62) cycles, profiles/r01_notes.md; using it picks the same tiles.)
-        cost = waves * (kblocks * 4 * max(bn // 2, 32) + 1500 + 12 * bn)
+        if old:
+            tiles = mt * (n // bn)
+            waves = -(-tiles // sms)
+            cost = waves * (kblocks * 4 * max(bn // 2, 32) + 1500 + 12 * bn)
+        else:
+            cost = unsplit_cost(n, mt, kblocks, bn, sms)
         if best_cost is None or cost < best_cost * 0.97:  # prefer wider tiles unless clearly slower
             best, best_cost = bn, cost
     return best

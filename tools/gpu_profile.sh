@@ -5,7 +5,7 @@
 mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
-K="regex:evc_gemm_kernel|gn_apply_kernel|gn_fir_kernel|evc_attn_kernel"
+K="regex:evc_gemm_kernel|gn_apply_kernel|gn_apply_stream_kernel|gn_fir_kernel|gn_fir_down_kernel|evc_attn_kernel"
 $CMD > gpurun_out/plain.log 2> gpurun_out/plain.err || { echo "plain run failed"; tail -5 gpurun_out/plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 520 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
