@@ -188,6 +188,16 @@ def test_tile_planning_host_logic():
     for n in (192, 384, 576, 768, 1152, 1536):
         bn = ops.pick_bn(n, ops.m_tiles(46, 8, 8, False), 108)
         assert n % bn == 0 and bn % 16 == 0
+    # more tiles than SMs even with the widest tile (6 videos at 64x64: 192 tiles): a narrower N tile re-reads the A tile
+    # in every round, so the widest one wins (profiles/r02_bn_probe.txt); with few tiles (6 videos at 16x16) the tile
+    # shrinks so that more SMs get work
+    assert ops.pick_bn(192, ops.m_tiles(6, 64, 64, False), 54, sms=148) == 192
+    assert ops.pick_bn(384, ops.m_tiles(6, 64, 64, False), 54, sms=148) == 192
+    assert ops.pick_bn(576, ops.m_tiles(6, 16, 16, False), 81, sms=148) < 192
+    # fused attention: head dims are multiples of 64 (128 between 256 and 384); larger heads split their output columns
+    assert ops.attn_supported(1024, 384, 2) and ops.attn_supported(64, 768, 4) and ops.attn_supported(4096, 384, 1)
+    assert ops.attn_supported(64, 768, 1) and ops.attn_supported(256, 1024, 2)  # unet.py 'deeper': one head of 768
+    assert not ops.attn_supported(100, 384, 2) and not ops.attn_supported(256, 320, 1) and not ops.attn_supported(256, 96, 1)
     # fused statistics need whole 32-row warp slices inside one sample; the fused GroupNorm apply whole 128-row tiles
     assert EngineBase.can_fuse_stats(128, 128) and EngineBase.can_fuse_stats(8, 8) and not EngineBase.can_fuse_stats(2, 2)
 
