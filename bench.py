@@ -269,7 +269,20 @@ def run_reference(args):
 
 def workload_config(args, world):
     per = "in total, sharded by video over the GPUs" if args.scaling == "strong" else "per GPU"
-    return {"workload": f"BASELINE.json configs[1]: city_bonn-shaped synthetic set, {args.videos} videos {per}, "
+    # which BASELINE.json config the arguments select (0-based indices as in BASELINE.json `configs`)
+    if args.model != "ncsnpp":
+        which = "configs[4] (models/unet.py variant)" + ("" if args.videos == 256 else f" at {args.videos} videos")
+    elif args.sampler == "ddpm" and args.subsample == 100 and args.videos == 46:
+        which = "configs[1]"
+    elif args.sampler == "fpndm" and args.subsample == 20 and args.videos == 512:
+        which = "configs[2]"
+    elif args.sampler == "ddim":
+        which = "configs[3] (DDIM step sweep)"
+    elif args.sampler == "ddpm" and args.subsample == 100 and args.videos == 1:
+        which = "configs[0] (one video per call)"
+    else:
+        which = "custom (not a BASELINE.json config)"
+    return {"workload": f"BASELINE.json {which}: city_bonn-shaped synthetic set, {args.videos} videos {per}, "
                         f"{args.sampler.upper()}-{args.subsample} ({EVALS[args.sampler](args.subsample)} UNet evaluations per "
                         f"cycle), {MODEL_NAME[args.model]}, random init, 5 predicted 128x128 frames per "
                         f"video per step",
@@ -452,10 +465,15 @@ def main():
         roofline = {"bound": "tensor", "kernel": "evc_gemm_kernel",
                     "launch": f"M={dom_key[0]} N={dom_key[1]} K={dom_key[2]} ({dom[0]} launches per evaluation, "
                               f"{dom[2] / dom[0] / 1e9:.1f} GFLOP each)",
-                    "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / pk["bf16_sustained"], "traffic": traffic, "traffic_source": traffic_src,
-                    "peak_source": pk["source"] + ", bf16 dense sustained",
-                    "all_gemm_launches": {"achieved": achieved_all, "frac": achieved_all / pk["bf16_sustained"],
+                    # per-launch CUDA events of an eager pass = kernels timed alone => the burst peak; the whole step
+                    # (`step_tensor_frac`, graph replay under the power cap) is held against the sustained one
+                    "achieved": achieved, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["bf16_burst"], "frac_of_sustained": achieved / pk["bf16_sustained"],
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": pk["source"] + ", bf16 dense burst (launches timed one by one); step_tensor_frac "
+                                   f"against the sustained figure {pk['bf16_sustained']}",
+                    "all_gemm_launches": {"achieved": achieved_all, "frac": achieved_all / pk["bf16_burst"],
+                                          "frac_of_sustained": achieved_all / pk["bf16_sustained"],
                                           "share_of_eval": gemm_ms / tot_ms},
                     "ms_per_eval_by_kernel": {k: round(v, 3) for k, v in by_kind.items()},
                     "batch_profiled": mb,
