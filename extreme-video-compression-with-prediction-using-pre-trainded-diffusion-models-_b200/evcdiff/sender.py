@@ -4,8 +4,11 @@ SenderCity.update / decide_5to5 (city_sender.py:353-437) and the `while x_ge.sha
 The reference handles one video at a time and round-trips every cycle through numpy.  Here all videos of a shard
 advance together: one captured sampling graph per cycle for the whole batch, PSNR and the accept-prefix decision
 on the GPU, frames resident in HBM.  Keyframe coding (ELIC, out of scope) is a caller-supplied callback; the
-default stand-in transmits the ground-truth frames unchanged.  The LPIPS variant (decide_5to5_lpips) needs AlexNet
-weights that are not in the image and is left to the reference.
+default stand-in transmits the ground-truth frames unchanged.  The accept decision is decide_5to5 (PSNR >= threshold,
+:353-374) by default; decide_5to5_lpips (:376-406: a perceptual distance <= threshold) is the same prefix rule with the
+comparison reversed, selected with `score_fn=..., higher_is_better=False` -- the LPIPS network itself (lpips==0.1.4,
+AlexNet weights, not in this image) is the caller's, e.g.
+`score_fn=lambda pred, gt: loss_fn_alex(pred.flatten(0, 1), gt.flatten(0, 1)).view(pred.shape[:2])`.
 """
 import torch
 
@@ -15,10 +18,15 @@ from .pipeline import generate_frame
 
 class BatchedSender:
     def __init__(self, net, config=None, threshold=20.0, sampler="DDPM", keyframe_fn=None, max_batch=64, compact=True,
-                 bucket=8, **sampler_kwargs):
+                 bucket=8, score_fn=None, higher_is_better=True, **sampler_kwargs):
         self.net = net
         self.config = config or net.config
         self.threshold = threshold
+        # per-frame score (pred, gt: (V, 5, 3, H, W) in [0,1] on the device) -> (V, 5); None = float64 PSNR on the GPU
+        # (cal_psnr, city_sender.py:255-258).  higher_is_better=False gives the `score <= threshold` rule of
+        # decide_5to5_lpips (city_sender.py:392)
+        self.score_fn = score_fn
+        self.higher_is_better = bool(higher_is_better)
         self.sampler = sampler
         self.keyframe_fn = keyframe_fn or (lambda frames_gt: frames_gt)  # ELIC stand-in: lossless keyframes
         self.max_batch = max_batch
@@ -68,8 +76,11 @@ class BatchedSender:
                 self.sampled_videos += V
             gidx = (pos[:, None] + torch.arange(self.num_frames, device=dev)[None, :]).clamp(max=x_gt.shape[1] - 1)
             gt = x_gt[ar[:, None], gidx]
-            psnr = ops.frame_psnr(pred.contiguous(), gt.contiguous())  # (V, 5) float64
-            acc = ops.accept_prefix(psnr, self.threshold, higher_is_better=True).long()
+            if self.score_fn is None:
+                score = ops.frame_psnr(pred.contiguous(), gt.contiguous())  # (V, 5) float64
+            else:
+                score = self.score_fn(pred, gt).to(torch.float64).reshape(V, self.num_frames)
+            acc = ops.accept_prefix(score, self.threshold, higher_is_better=self.higher_is_better).long()
             acc = torch.where(pos < T, acc, torch.zeros_like(acc))
             for j in range(self.num_frames):  # accepted prefix -> reconstruction, flag 0
                 take = (acc > j) & (pos + j < T)

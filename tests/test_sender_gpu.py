@@ -69,11 +69,19 @@ def _fake_predictor(cond01):
     return torch.stack(frames, 1)  # (B, 5, 3, H, W)
 
 
+def _fake_distance(p, g):
+    """Stand-in for loss_fn_alex (city_sender.py:302,389; the AlexNet LPIPS weights are not in the image): a distance that
+    is 0 for equal frames and grows with the difference, float64 so that the batched and the per-frame evaluation agree."""
+    return (p.double() - g.double()).abs().mean(dim=(-3, -2, -1))
+
+
+@pytest.mark.parametrize("rule", ["psnr", "lpips"])
 @pytest.mark.parametrize("compact", [False, True])
-def test_batched_sender_equals_reference_loop_per_video(monkeypatch, compact):
-    """BatchedSender against oracle/sender.py (restatement of SenderCity.update / decide_5to5 and the driver's while loop,
-    city_sender.py:353-437, 519-550), video by video: same flags d, same reconstruction x_ge, same number of cycles for the
-    slowest video -- with and without compaction of finished videos."""
+def test_batched_sender_equals_reference_loop_per_video(monkeypatch, compact, rule):
+    """BatchedSender against oracle/sender.py (restatement of SenderCity.update / decide_5to5 / decide_5to5_lpips and the
+    driver's while loop, city_sender.py:353-437, 519-550), video by video: same flags d, same reconstruction x_ge, same
+    number of cycles for the slowest video -- with and without compaction of finished videos, for the PSNR rule (score >=
+    threshold) and the LPIPS rule (distance <= threshold, injected distance)."""
     from evcdiff import sender as S
     from oracle import sender as RS
     calls = []
@@ -88,14 +96,17 @@ def test_batched_sender_equals_reference_loop_per_video(monkeypatch, compact):
     drift = torch.linspace(0.002, 0.03, V, device=DEV).view(V, 1, 1, 1, 1) * torch.arange(T, device=DEV).view(1, T, 1, 1, 1)
     x_gt = (base * (0.4 + 0.6 * torch.rand(V, 1, 1, 1, 1, device=DEV, generator=g)) + drift).clamp(0, 1)
     cfg = common.gpu64_config(device=DEV)
-    thr = 31.0
-    snd = S.BatchedSender(None, cfg, threshold=thr, compact=compact, bucket=4)
+    if rule == "psnr":
+        thr, kw, lp = 31.0, {}, None
+    else:
+        thr, kw, lp = 0.02, dict(score_fn=_fake_distance, higher_is_better=False), (lambda p, g: float(_fake_distance(p, g)))
+    snd = S.BatchedSender(None, cfg, threshold=thr, compact=compact, bucket=4, **kw)
     x_ge, d, n = snd.encode(x_gt)
     x_ge, d = x_ge.cpu(), d.cpu().numpy()
     cycles = []
     for v in range(V):
         gf = lambda frames: _fake_predictor(frames.to(DEV)).cpu()
-        r_ge, r_d, r_n = RS.encode_video(x_gt[v].cpu(), gf, thr, total=T)
+        r_ge, r_d, r_n = RS.encode_video(x_gt[v].cpu(), gf, thr, total=T, lpips_fn=lp)
         assert d[v].tolist() == r_d.tolist(), (v, d[v].tolist(), r_d.tolist())
         assert torch.equal(x_ge[v], r_ge.float()), v
         cycles.append(r_n)
