@@ -28,7 +28,8 @@ class BatchedSender:
         self.score_fn = score_fn
         self.higher_is_better = bool(higher_is_better)
         self.sampler = sampler
-        self.keyframe_fn = keyframe_fn or (lambda frames_gt: frames_gt)  # ELIC stand-in: lossless keyframes
+        # (n, 3, H, W) frames in [0,1] -> decoded frames of the same shape; ELIC stand-in: lossless keyframes
+        self.keyframe_fn = keyframe_fn or (lambda frames_gt: frames_gt)
         self.max_batch = max_batch
         # finished videos leave the sampling batch (the reference stops calling update() for a video that has its 30
         # frames, city_sender.py:534); the active set is padded to a multiple of `bucket` so that only a few batch
@@ -52,7 +53,8 @@ class BatchedSender:
         x_ge = torch.zeros((V, T + self.num_frames + self.num_cond, C, H, W), dtype=torch.float32, device=dev)
         d = torch.ones((V, T + self.num_frames + self.num_cond), dtype=torch.int32, device=dev)
         pos = torch.full((V,), self.num_cond, dtype=torch.long, device=dev)  # frames available per video
-        x_ge[:, :self.num_cond] = self.keyframe_fn(x_gt[:, :self.num_cond])
+        x_ge[:, :self.num_cond] = self.keyframe_fn(x_gt[:, :self.num_cond].reshape(-1, C, H, W)).reshape(
+            V, self.num_cond, C, H, W)  # keyframe_fn always sees (n, 3, H, W) frames
         ar = torch.arange(V, device=dev)
         n_cycles = 0
         while bool((pos < T).any()):
