@@ -79,6 +79,24 @@ def test_eps_b46_every_sample(full, cta_group, monkeypatch):
     assert torch.equal(e46, net(x, torch.full((B,), 500, dtype=torch.long, device=DEV), cond=cond))
 
 
+@pytest.mark.parametrize("B", [5, 11, 12, 23])
+def test_eps_per_gpu_shares_of_the_46_video_set(full, B):
+    """The batch sizes a rank is left with when `bench.py --gpus N` shards the 46 videos (pipeline.shard_range): 23 at
+    N=2, 12 / 11 at N=4, 6 / 5 at N=8 (6 is covered by the DDPM-100 test below).  Every batch size has its own tile / split-K /
+    CTA-pair choices (ops.pick_tile), so each one is checked sample by sample against the oracle."""
+    cfg, net, sd = full
+    g = torch.Generator(device=DEV).manual_seed(100 + B)
+    x = torch.randn(B, 15, 128, 128, device=DEV, generator=g)
+    cond = torch.rand(B, 6, 128, 128, device=DEV, generator=g, dtype=torch.float64) * 2 - 1
+    labels = torch.full((B,), 500, dtype=torch.long, device=DEV)
+    eps = net(x, labels, cond=cond)
+    assert torch.isfinite(eps).all()
+    errs = _per_sample_err(eps, _oracle_eps(sd, cfg, x, labels, cond))
+    assert max(errs) < EPS_TOL, (B, max(errs), errs)
+    assert torch.equal(eps, net(x, labels, cond=cond))  # same bits when repeated
+    net.unet._engines.pop((B, str(torch.device("cuda", torch.cuda.current_device())), "bf16"), None)  # free its buffers
+
+
 @pytest.mark.parametrize("B", [1, 6])
 def test_ddpm100_full_model(full, B):
     """north_star's literal condition on the benchmarked network: 100-step DDPM (101 evaluations), same noise tape.
