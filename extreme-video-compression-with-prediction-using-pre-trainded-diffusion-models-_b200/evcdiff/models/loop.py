@@ -49,9 +49,10 @@ class SamplerLoop:
 
     def _capture_or_run(self, key, body, graph):
         """body() enqueues the loop on the current stream.  With graph=True it is captured once and replayed."""
-        # small batches are launch-latency bound: overlap kernel prologues with programmatic dependent launch
+        # small batches are launch-latency bound: overlap kernel prologues with programmatic dependent launch (same-box A/B,
+        # profiles/r02_notes.md: +4 % at 1 video, +0.4-1.1 % at 12, neutral at 23, -0.7 % at 46)
         pixels = self.x.shape[0] * self.x.shape[2] * self.x.shape[3]
-        _lib.load().evc_set_pdl(1 if pixels <= 8 * 128 * 128 else 0)
+        _lib.load().evc_set_pdl(1 if pixels <= 16 * 128 * 128 else 0)
         if not graph:
             n0 = ops.launch_count()
             body()
