@@ -252,3 +252,40 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"] and line["vs_baseline"] is None
+
+
+# every conv3x3 / 1x1 launch shape of one NCSN++ evaluation at 128x128, (Cin, Cout, H)
+_CONV3 = [(192, 192, 128), (384, 192, 128), (192, 192, 64), (384, 384, 64), (384, 192, 64), (576, 192, 64), (192, 192, 32),
+          (192, 384, 32), (384, 384, 32), (576, 576, 32), (576, 384, 32), (768, 384, 32), (960, 384, 32), (384, 384, 16),
+          (384, 576, 16), (576, 576, 16), (768, 768, 16), (960, 576, 16), (1152, 576, 16), (1344, 576, 16), (576, 576, 8),
+          (576, 768, 8), (768, 768, 8), (1344, 768, 8), (1536, 768, 8)]
+_CONV1 = [(384, 1152, 32), (576, 1728, 16), (768, 2304, 8), (384, 384, 32), (576, 576, 16), (768, 768, 8)]  # q|k|v and NIN_3
+
+
+def test_tile_choice_invariants_for_every_batch_size():
+    """ops.pick_tile for every per-GPU batch a sharded run can produce (1..64 videos) and every launch shape of the model:
+    the N tile divides N, split-K only where the kernel supports it (32-column chunks, >= 4 K blocks per slice, every
+    slice resident, partial tiles inside the workspace), and the fused-GroupNorm guard mirrors its two-round rule."""
+    from evcdiff import ops
+    sms = 148
+    for B in range(1, 65):
+        for taps, shapes in ((9, _CONV3), (1, _CONV1)):
+            for cin, cout, h in shapes:
+                mt = ops.m_tiles(B, h, h, False)
+                assert mt == -(-B * h * h // 128) or h < 16  # whole images share a tile only below 128 pixels per image
+                kblocks = taps * cin // 64
+                bn, S = ops.pick_tile(cout, mt, kblocks, sms=sms)
+                assert cout % bn == 0 and bn % 16 == 0 and bn <= 256, (B, cin, cout, h, bn)
+                assert S >= 1
+                if S > 1:
+                    tiles = mt * (cout // bn)
+                    assert bn % 32 == 0 and kblocks // S >= 4 and tiles * S <= sms, (B, cin, cout, h, bn, S)
+                    assert S * ((mt + 1) // 2 * 2) * 128 * cout * 4 <= ops.SPLIT_K_WS_BYTES
+                    assert mt * (cout // 256 if cout % 256 == 0 else 1) < sms  # never for launches that fill the GPU
+                # the unsplit choice is what pick_bn alone gives
+                if S == 1:
+                    assert bn == ops.pick_bn(cout, mt, kblocks, sms)
+    # fused GroupNorm apply: a sample's tiles must fit in two rounds of the persistent grid (gemm_tc.cu plan guard)
+    assert ops.gn_fuse_fits(128, 46 * 128, 1, sms=sms) and ops.gn_fuse_fits(128, 128, 1, sms=sms)
+    assert not ops.gn_fuse_fits(512, 512, 1, sms=sms)      # image_size 256: 512 tiles per sample > 2 x 148
+    assert not ops.gn_fuse_fits(128, 128, 1, sms=40)       # a reduced SM count breaks the rule as well
