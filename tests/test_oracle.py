@@ -188,3 +188,56 @@ def test_sender_restatement_invariants():
     assert d[:7].tolist() == [1, 1, 0, 0, 0, 1, 1]
     a, b = np.zeros((3, 4, 4)), np.full((3, 4, 4), 0.1)
     assert abs(RS.cal_psnr(a, b) - 20.0) < 1e-9
+
+
+_LIVE = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])          # tests/golden
+import make_golden as M                   # imports the UNMODIFIED reference from EVC_REF (default /root/reference)
+import common
+out = {}
+cfg = common.tiny_config()
+net, _ = M.build_ref(cfg, seed=1, active=True)
+for k in ("betas", "alphas", "alphas_prev"):
+    out["sched_" + k] = getattr(net, k).numpy()
+t = torch.tensor([0.0, 10.0, 990.0, 999.0, -0.5, 25.0, -1.0])
+out["temb_192"] = M.ref_temb(t, 192).numpy()
+g = torch.Generator().manual_seed(5)
+xf = torch.randn(2, 5, 8, 8, generator=g)
+out["fir_up"] = M.ref_updown.upsample_2d(xf, (1, 3, 3, 1), factor=2).numpy()
+out["fir_down"] = M.ref_updown.downsample_2d(xf, (1, 3, 3, 1), factor=2).numpy()
+alphas_old = net.alphas.flip(0)
+xt = torch.randn(2, 15, 4, 4, generator=g)
+et = torch.randn(2, 15, 4, 4, generator=g)
+out["transfer_out"] = M.ref_pndm.transfer(xt, torch.tensor([50.0, 50.0]), torch.tensor([25.0, 25.0]), et, alphas_old,
+                                          clip_before=True).numpy()
+g = torch.Generator().manual_seed(2)
+x = torch.randn(2, 15, 16, 16, generator=g)
+cond = torch.rand(2, 6, 16, 16, generator=g, dtype=torch.float64) * 2 - 1
+with torch.no_grad():
+    out["tiny_act_eps_500"] = net(x, torch.full((2,), 500, dtype=torch.long), cond=cond).numpy()
+    out["tiny_act_eps_m0p5"] = net(x, torch.full((2,), -0.5), cond=cond).numpy()
+np.savez(sys.argv[2], **out)
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("EVC_REF", "/root/reference")),
+                    reason="the reference tree only exists in the build container")
+def test_goldens_reproduce_from_the_live_reference(small, tmp_path):
+    """The committed fixtures ARE the reference's outputs: a subset (schedule, time embedding, FIR up / down, pndm.transfer,
+    eps at an integer and at the fractional F-PNDM label) is regenerated here from the unmodified reference, in a separate
+    process (its top-level package is called `models`, like ours), and compared with tests/golden/ncsnpp_small.npz."""
+    import subprocess
+    import sys
+    dst = str(tmp_path / "live.npz")
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, "-c", _LIVE, G, dst], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    live = dict(np.load(dst))
+    for k, v in live.items():
+        ref = small[k]
+        assert v.shape == ref.shape and v.dtype == ref.dtype, k
+        if k.startswith("sched_"):
+            assert np.array_equal(v, ref), k
+        else:  # same torch build and thread count as the generator run: equal up to reduction-order noise
+            assert common.rel_l2(T(v), T(ref)) < 1e-6, (k, common.rel_l2(T(v), T(ref)))
