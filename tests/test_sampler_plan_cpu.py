@@ -150,3 +150,36 @@ def test_fpndm_plan_equals_oracle(monkeypatch, subsample, clip):
     M = _install(monkeypatch, eng2)
     allx = M.FPNDM_sampler(x_T.clone(), net, cond=cond, final_only=False, subsample_steps=subsample, clip_before=clip)
     assert allx.shape == (subsample, B, 15, H, H) and torch.equal(allx[-1], got[0])
+
+
+def test_generate_frame_micro_batches_host_logic(monkeypatch):
+    """pipeline.generate_frame (city_sender.py:326-351) on CPU with a recording sampler: data_transform 2x-1 on the
+    conditioning frames (dtype kept, like the reference's float64 input), per-micro-batch slices of the caller's x_T and of
+    every noise draw, inverse transform + clamp, (B, 5, 3, H, W) result -- whatever max_batch is."""
+    from evcdiff import pipeline as P
+    cfg = common.tiny_config()
+    H = cfg.data.image_size
+    monkeypatch.setattr(P.ops, "inverse_transform", lambda x, out: out.copy_(((x + 1.0) / 2.0).clamp(0, 1)))
+    calls = []
+
+    def sampler(x_T, net, cond=None, noise=None, **kw):
+        calls.append((x_T.shape[0], cond.dtype, kw.get("subsample_steps"), kw.get("final_only")))
+        assert cond.shape[0] == x_T.shape[0] and all(n.shape[0] == x_T.shape[0] for n in noise)
+        out = 0.5 * x_T + 0.25 * cond.float().mean(dim=1, keepdim=True) + sum(noise)
+        return out.unsqueeze(0)
+
+    net = torch.nn.Linear(1, 1)  # only `next(net.parameters()).device` is used by the glue
+    g = torch.Generator().manual_seed(5)
+    B = 7
+    frames_in = torch.rand(B, 6, H, H, generator=g, dtype=torch.float64)
+    x_T = torch.randn(B, 15, H, H, generator=g)
+    noise = [0.01 * torch.randn(B, 15, H, H, generator=g) for _ in range(3)]
+    one = P.generate_frame(net, frames_in, config=cfg, sampler=sampler, init_samples=x_T, noise=noise, max_batch=64)
+    assert one.shape == (B, cfg.data.num_frames, cfg.data.channels, H, H) and one.device.type == "cpu"
+    assert float(one.min()) >= 0.0 and float(one.max()) <= 1.0
+    want = ((0.5 * x_T + 0.25 * (2 * frames_in - 1).float().mean(dim=1, keepdim=True) + sum(noise) + 1) / 2).clamp(0, 1)
+    assert torch.allclose(one.reshape(B, 15, H, H), want, atol=1e-6)
+    assert calls == [(B, torch.float64, cfg.sampling.subsample, True)]
+    calls.clear()
+    parts = P.generate_frame(net, frames_in, config=cfg, sampler=sampler, init_samples=x_T, noise=noise, max_batch=3)
+    assert [c[0] for c in calls] == [3, 3, 1] and torch.equal(parts, one)
